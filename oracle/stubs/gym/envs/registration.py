@@ -1,0 +1,6 @@
+"""gym.envs.registration stand-in (test infrastructure only)."""
+registry = {}
+
+
+def register(id, entry_point=None, **kwargs):
+    registry[id] = (entry_point, kwargs)

@@ -1,0 +1,9 @@
+"""gym.utils.seeding stand-in (test infrastructure only)."""
+import numpy as np
+
+
+def np_random(seed=None):
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy % (2 ** 31))
+    rng = np.random.RandomState(int(seed) % (2 ** 32))
+    return rng, seed
