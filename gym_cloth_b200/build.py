@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Build gym_cloth_b200/libclothb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m gym_cloth_b200.build [--force] [--verbose]
+
+Three translation units: cloth_f32.cu (production), cloth_f64.cu (parity build, -fmad=false so
+that every operator is one rounded IEEE operation) and cloth_abi.cu (extern "C" surface).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libclothb200.so")
+OBJ = os.path.join(HERE, "csrc", "_build")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+UNITS = [("cloth_f32.cu", []), ("cloth_f64.cu", ["-fmad=false"]), ("cloth_abi.cu", [])]
+
+
+def _newest_src():
+    t = 0
+    for root, _, files in os.walk(CSRC):
+        if "_build" in root:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h")):
+                t = max(t, os.path.getmtime(os.path.join(root, f)))
+    t = max(t, os.path.getmtime(os.path.join(HERE, "..", "include", "clothb200.h")))
+    return t
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_src():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    procs = []
+    objs = []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            print(" ".join(cmd)); print(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed for %s" % cmd[-3])
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,296 @@
+// cloth_kernels.cuh - __global__ entry points and host launchers, templated on the scalar type.
+// Included by cloth_f32.cu (production, FMA contraction on) and cloth_f64.cu (parity build, -fmad=false).
+#pragma once
+#include <atomic>
+#include <cstdio>
+
+#include "cloth_device.cuh"
+
+namespace clothb200 {
+
+extern std::atomic<long long> g_launch_count;   // defined in cloth_abi.cu
+void set_cuda_error(cudaError_t e, const char *where);
+
+// ------------------------------------------------------------------------------------------------
+// The action kernel: one CTA = one cloth = one whole ClothEnv.step (or n bare updates).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NT, int WC, bool REST_TABLE>
+__global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ DevParams<T> P, const __grid_constant__ StepArgs<T> A) {
+    typedef ClothCTA<T, NT, WC, REST_TABLE> CTA;
+    typedef typename CTA::P4 P4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int env = A.env_order ? A.env_order[blockIdx.x] : (int)blockIdx.x;
+    const int tid = threadIdx.x;
+    const T *rest_env = REST_TABLE ? A.rest + (long long)env * A.rest_env_stride : nullptr;
+    CTA c(P, smem, rest_env);
+    const int N = c.N;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + CTA::smem_bytes(N, P.table_size, P.ev_words) - 16);
+    const uint32_t bytes = (uint32_t)(sizeof(P4) * (size_t)N);
+    T *gpos = A.pos + (size_t)env * N * 4, *gprev = A.prev + (size_t)env * N * 4;
+
+    // ---- stage the cloth into shared memory: two TMA bulk copies completing on one mbarrier ----
+    if (tid == 0) mbar_init(bar, 1);
+    c.sync();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(c.pos, gpos, bytes, bar);
+        bulk_g2s(c.prev, gprev, bytes, bar);
+    }
+    for (int j = tid; j < P.table_size; j += NT) { c.tkey[j] = CLOTH_KEY_EMPTY; c.tinfo[j] = 0u; }
+    for (int j = tid; j < P.ev_words; j += NT) c.ev[j] = 0u;
+    if (tid < 16) c.misc[tid] = 0;
+    int flags_in = A.flags ? A.flags[env] : 0;
+    mbar_wait(bar, 0);
+    c.sync();
+    if (tid == 0) c.misc[2] = (flags_in & CLOTHB200_FLAG_TEAR) ? 1 : 0;
+    if (tid == 0 && (flags_in & CLOTHB200_FLAG_BADSTATE)) c.misc[3] = 1;
+    c.sync();
+
+    int nupd = 0, ngrab = -1, iters_pull = 0;
+    if (A.mode == KMODE_STEP) {
+        const ClothB200Plan plan = A.plans[env];
+        iters_pull = plan.iters_pull;
+        ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
+        if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+        // _pull thresholds (cloth_env.py:352-367, 472-475): `i < t` for integer i <=> i < ceil(t)
+        const double iu = A.iters_up_env ? A.iters_up_env[env] : P.iu;
+        const double t1 = iu + P.iur, t2 = t1 + (double)plan.iters_pull, t3 = t2 + P.igr, t4 = t3 + P.ir;
+        const int e0 = (int)ceil(iu), e1 = (int)ceil(t1), e2 = (int)ceil(t2), e3 = (int)ceil(t3);
+        const int iterations = ngrab == 0 ? 0 : (int)ceil(t4);   // cloth_env.py:490-493
+        const T dxr = (T)plan.dxr, dyr = (T)plan.dyr;
+        bool released = false;
+        for (int i = 0; i < iterations; i++) {
+            if (i < e0) { c.gripper_adjust(T(0.0), T(0.0), T(0.0025)); c.sync(); }
+            else if (i < e1) { }
+            else if (i < e2) { c.gripper_adjust(dxr, dyr, T(0.0)); c.sync(); }
+            else if (i < e3) { }
+            else if (!released) { c.gripper_release(); released = true; c.sync(); }
+            c.update_reference_order();
+            nupd++;
+            if (c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
+        }
+    } else if (A.mode == KMODE_UPDATE) {
+        for (int i = 0; i < A.n_updates; i++) c.update_reference_order();
+        nupd = A.n_updates;
+    } else if (A.mode == KMODE_GRAB) {
+        ngrab = c.grab_top(A.grab_xy[2 * env], A.grab_xy[2 * env + 1], A.grab_radius);
+        if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+    }
+
+    // ---- reward terms ----
+    const bool want_measure = (A.coverage || A.variance_inv || A.reward) && A.mode != KMODE_GRAB;
+    double cov = 0.0, vinv = 0.0;
+    const bool oob = c.out_of_bounds();
+    if (want_measure) {
+        vinv = c.variance_inv();
+        cov = c.hull_area();
+    }
+    const int tear = c.misc[2], bad = c.misc[3];
+    c.sync();
+
+    // ---- write back: state via TMA bulk store, scalars by thread 0 ----
+    if (A.mode != KMODE_MEASURE) {
+        fence_async_smem();
+        c.sync();
+        if (tid == 0) {
+            bulk_s2g(gpos, c.pos, bytes);
+            bulk_s2g(gprev, c.prev, bytes);
+            bulk_commit_wait();
+        }
+    }
+    if (A.obs) {
+        const T *flat = reinterpret_cast<const T *>(c.pos);
+        T *o = A.obs + (size_t)env * 3 * N;
+        for (int i = tid; i < 3 * N; i += NT) { const int p = i / 3; o[i] = flat[p * 4 + (i - p * 3)]; }
+    }
+    if (tid == 0) {
+        int f = (tear ? CLOTHB200_FLAG_TEAR : 0) | (oob ? CLOTHB200_FLAG_OOB : 0) | (bad ? CLOTHB200_FLAG_BADSTATE : 0);
+        if (A.mode == KMODE_STEP && ngrab == 0) f |= CLOTHB200_FLAG_NOGRAB;
+        if (A.flags) A.flags[env] = f;
+        if (A.sim_steps) A.sim_steps[env] = nupd;
+        if (A.n_grabbed && ngrab >= 0) A.n_grabbed[env] = ngrab;
+        if (want_measure) {
+            if (A.coverage) A.coverage[env] = cov;
+            if (A.variance_inv) A.variance_inv[env] = vinv;
+        }
+        if (A.mode == KMODE_STEP && A.reward && !A.initialize) {
+            // ClothEnv.step bookkeeping + _reward + _terminal (cloth_env.py:519-521, 536-715), reward_type coverage-delta
+            const int steps = A.num_steps[env] + 1;
+            A.num_steps[env] = steps;
+            A.num_sim_steps[env] += nupd;
+            double rew = 0;
+            if (tear) rew += 0.0; else if (oob) rew += 0.0;
+            if (ngrab == 0) rew += -0.01;
+            if (cov > 0.92) rew += 5.;
+            rew += 0.0;
+            const double prevc = A.prev_coverage[env];
+            rew += cov - prevc;
+            A.prev_coverage[env] = cov;
+            A.reward[env] = rew;
+            A.done[env] = (steps >= P.max_actions) || tear || oob || (cov > 0.92);
+        }
+    }
+    (void)iters_pull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------
+// ClothEnv.step action decode (cloth_env.py:401-470) with x*x for `**2`
+template <typename T>
+__global__ void decode_actions_kernel(int n, const T *__restrict__ actions, ClothB200Plan *__restrict__ plans, int clip_act_space,
+                                      int delta_actions, double reduce_factor, int iters_pull_max) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double lo[4], hi[4];
+    const double pi_f32 = 3.1415927410125732;
+    if (clip_act_space) { for (int i = 0; i < 4; i++) { lo[i] = -1.0; hi[i] = 1.0; } }
+    else if (delta_actions) { lo[0] = 0; lo[1] = 0; lo[2] = -1; lo[3] = -1; hi[0] = hi[1] = hi[2] = hi[3] = 1; }
+    else { lo[0] = -0.25; lo[1] = -0.25; lo[2] = 0.0; lo[3] = -pi_f32; hi[0] = 1.25; hi[1] = 1.25; hi[2] = 1.0; hi[3] = pi_f32; }
+    double a[4];
+    for (int i = 0; i < 4; i++) {
+        double v = (double)actions[4 * e + i];
+        double m = (hi[i] < v) ? hi[i] : v;
+        a[i] = (lo[i] > m) ? lo[i] : m;
+    }
+    double x = a[0], y = a[1], length = a[2], radians = a[3];
+    if (clip_act_space) {
+        x = (x / 2.0) + 0.5; y = (y / 2.0) + 0.5;
+        if (!delta_actions) { length = (length / 2.0) + 0.5; radians = radians * 3.141592653589793; }
+    }
+    double xd, yd, total = 0.0;
+    if (delta_actions) {
+        total = sqrt(a[2] * a[2] + a[3] * a[3]);
+        xd = a[2] / (total + 1e-5); yd = a[3] / (total + 1e-5);
+    } else { xd = cos(radians); yd = sin(radians); }
+    const double xr = xd * reduce_factor, yr = yd * reduce_factor;
+    int ip;
+    if (delta_actions) {
+        const double stepl = sqrt(xr * xr + yr * yr);
+        int ii = 0;
+        if (stepl > 0.0) { double cur = 0; for (;;) { cur += stepl; if (cur >= total) break; ii += 1; } }
+        ip = ii;
+    } else ip = (int)(iters_pull_max * length);
+    ClothB200Plan pl; pl.gx = x; pl.gy = y; pl.dxr = xr; pl.dyr = yr; pl.iters_pull = ip; pl.reserved = 0;
+    plans[e] = pl;
+}
+
+template <typename T>
+__global__ void broadcast_state_kernel(int n4, int n_env, const T *__restrict__ pos4, const T *__restrict__ prev4, T *__restrict__ pos,
+                                       T *__restrict__ prev) {
+    const size_t total = (size_t)n4 * n_env;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % n4);
+        pos[i] = pos4[j];
+        prev[i] = prev4[j];
+    }
+}
+
+// Gripper.adjust / release over a batch (facade-level calls; the step kernel has its own in-smem versions)
+template <typename T>
+__global__ void gripper_adjust_kernel(size_t total_pts, T dx, T dy, T dz, T *__restrict__ pos, T *__restrict__ prev) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= total_pts) return;
+    T *p = pos + 4 * i, *q = prev + 4 * i;
+    const int m = (int)q[3];
+    for (int r = 0; r < m; r++) {
+        q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+        p[0] = dx + p[0]; p[1] = dy + p[1]; p[2] = dz + p[2];
+    }
+}
+template <typename T> __global__ void gripper_release_kernel(size_t total_pts, T *__restrict__ pos, T *__restrict__ prev) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= total_pts) return;
+    if (prev[4 * i + 3] > T(0)) { pos[4 * i + 3] = T(0); prev[4 * i + 3] = T(0); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T> &P) {
+    const int W = hp.num_width_points, H = hp.num_height_points;
+    P.W = W; P.H = H; P.N = W * H;
+    int ts = 64; while (ts < (P.N * 8 + 4) / 5) ts <<= 1;   // >= 1.6 N
+    P.table_size = ts;
+    int sh = 0; while ((1 << sh) < ts) sh++;
+    P.table_shift = 32 - sh;
+    P.ev_words = (6 * P.N + 31) / 32;
+    P.max_actions = hp.max_actions;
+    // constants exactly as cloth.pyx:175-186, 240-241 derive them, in double, then rounded to T once
+    const double mass = hp.density / W / H;
+    const double delta_t = 1.0 / hp.frames_per_sec / hp.simulation_steps;
+    P.mg = (T)(mass * hp.gravity);
+    P.kk_struct = (T)(hp.ks * 1.0);
+    P.kk_bend = (T)(hp.ks * 0.2);
+    P.dsdm = (T)((delta_t * delta_t) / mass);
+    P.damp = (T)(1.0 - hp.damping / 100.0);
+    const double dx = hp.width * 1.0 / (W - 1), dy = hp.height * 1.0 / (H - 1);
+    const double cw = 3 * dx, ch = 3 * dy;
+    P.cell_w = (T)cw; P.cell_h = (T)ch; P.cell_t = (T)(cw > ch ? cw : ch);
+    P.thresh = (T)(2.0 * hp.thickness);
+    P.sim_steps = (T)hp.simulation_steps;
+    P.min_z = (T)hp.minimum_z;
+    P.fric1 = (T)(1. - hp.plane_friction);
+    P.surf_off = (T)0.0001;
+    P.tear_thresh = (T)hp.tear_thresh;
+    const double diag = sqrt(dx * dx + dy * dy);
+    const double rk[6] = {dx, dy, diag, diag, 2 * dx, 2 * dy};
+    for (int k = 0; k < 6; k++) P.rest_k[k] = (T)rk[k];
+    P.grip_radius = hp.grip_radius; P.thickness = hp.thickness; P.gripper_height = hp.gripper_height;
+    int nlev = 0;
+    for (double z = hp.gripper_height; z > 0; z -= hp.thickness) { nlev++; if (nlev > 4 * ts / 8) break; }
+    P.n_levels = nlev;
+    P.iu = hp.iters_up; P.iur = hp.iters_up_rest; P.igr = hp.iters_grip_rest; P.ir = hp.iters_rest;
+    return 0;
+}
+
+template <typename T, int NT, int WC, bool RT> int launch_step_inst(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
+    typedef ClothCTA<T, NT, WC, RT> CTA;
+    const size_t smem = CTA::smem_bytes(P.N, P.table_size, P.ev_words);
+    auto kern = cloth_step_kernel<T, NT, WC, RT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(smem)"); return CLOTHB200_ERR_UNSUPPORTED; }
+        configured = smem;
+    }
+    kern<<<A.n_env, NT, smem, st>>>(P, A);
+    g_launch_count++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_cuda_error(e, "cloth_step_kernel launch"); return CLOTHB200_ERR_CUDA; }
+    return CLOTHB200_OK;
+}
+
+int threads_per_cloth();   // cloth_abi.cu: CLOTHB200_NT env var, default 128
+
+template <typename T, int WC, bool RT> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
+    switch (threads_per_cloth()) {
+        case 32: return launch_step_inst<T, 32, WC, RT>(P, A, st);
+        case 64: return launch_step_inst<T, 64, WC, RT>(P, A, st);
+        case 256: return launch_step_inst<T, 256, WC, RT>(P, A, st);
+        default: return launch_step_inst<T, 128, WC, RT>(P, A, st);
+    }
+}
+
+template <typename T> int launch_step(const ClothB200Params &hp, const StepArgs<T> &A, cudaStream_t st) {
+    if (A.n_env == 0) return CLOTHB200_OK;
+    DevParams<T> P;
+    make_dev_params(hp, P);
+    if (P.N >= 32768) return CLOTHB200_ERR_UNSUPPORTED;   // 15-bit slots / 16-bit indices
+    const bool rt = A.rest != nullptr;
+    if (!rt && sizeof(T) == 8) return CLOTHB200_ERR_ARG;  // the parity build always takes the exact rest table
+    if (P.W == 25 && P.H == 25) {
+        if (rt) return launch_step_nt<T, 25, true>(P, A, st);
+        return launch_step_nt<T, 25, false>(P, A, st);
+    }
+    if (rt) return launch_step_nt<T, 0, true>(P, A, st);
+    return launch_step_nt<T, 0, false>(P, A, st);
+}
+
+template <typename T> size_t step_smem_bytes(const ClothB200Params &hp) {
+    DevParams<T> P;
+    make_dev_params(hp, P);
+    return ClothCTA<T, 128, 0, true>::smem_bytes(P.N, P.table_size, P.ev_words);
+}
+
+}  // namespace clothb200

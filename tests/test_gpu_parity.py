@@ -1,0 +1,279 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libclothb200.so via gym_cloth_b200.batched.BatchedCloth.
+
+  f64 build  : BIT-EXACT against the golden fixtures produced by the reference itself and against the
+               CPU oracle on seeded random inputs (positions, previous positions, pinned/grabbed sets,
+               substep counts, tear flags); coverage |d| <= 1e-12, variance_inv rel <= 1e-12.
+  f32 build  : same ordering, float arithmetic.  Tolerances (measured FP32-vs-FP64
+               divergence of this chaotic system), from a shared start state:
+                 one Cloth.update():  max |dpos| <= 2e-6
+                 one whole action  :  max |dpos| <= 2e-2, mean |dpos| <= 1e-3, |dcoverage| <= 5e-3,
+                                      identical substep counts and grabbed sets.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle.oracle import OracleCloth, params_from_cfg as oracle_params  # noqa: E402  (checker only)
+
+
+def _lib():
+    from gym_cloth_b200 import lib
+    return lib
+
+
+def _bc(n_env, dtype, **kw):
+    from gym_cloth_b200 import lib
+    from gym_cloth_b200.batched import BatchedCloth
+    return BatchedCloth(lib.default_params(), n_env, dtype=dtype, **kw)
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------------------------- f64: goldens
+def test_f64_kat_appendix_d():
+    g = load_golden("kat_appendix_d.npz")
+    bc = _bc(2, torch.float64)
+    bc.grab_top((0.5, 0.5))
+    assert bc.grabbed_set(0).tolist() == g["grabbed"].tolist()
+    assert bc.n_grabbed.cpu().tolist() == [5, 5]
+    n = 0
+
+    def run(k, adj=None):
+        nonlocal n
+        for _ in range(k):
+            if adj is not None:
+                bc.adjust(*adj)
+            bc.update(1)
+            n += 1
+            if "pos_%d" % n in g.files:
+                for e in (0, 1):
+                    pos, prev, pin, _ = bc.get_state(e)
+                    assert _eq(pos, g["pos_%d" % n]), (n, np.abs(pos - g["pos_%d" % n]).max())
+                    assert _eq(prev, g["prev_%d" % n]), n
+                    assert _eq(pin, g["pin_%d" % n].astype(bool)), n
+
+    run(50, (0, 0, 0.0025)); run(80); run(100, (0.002 * 0.6, 0.002 * 0.8, 0)); run(300)
+    bc.release(); run(1000)
+    bc.measure(); _sync()
+    assert abs(bc.coverage[0].item() - float(g["coverage"])) < 1e-12
+    assert bc.flags.cpu().tolist() == [0, 0]
+
+
+def test_f64_phases_one_update():
+    g = load_golden("phases.npz")
+    bc = _bc(1, torch.float64)
+    bc.set_state(g["pos_0"], g["prev_0"], g["pin_0"], grabbed=g["grabbed"])
+    bc.adjust(0.0016, -0.0012, 0.0)
+    pos, prev, _, _ = bc.get_state()
+    assert _eq(pos, g["pos_adjust"]) and _eq(prev, g["prev_adjust"])
+    bc.update(1)
+    pos, prev, _, _ = bc.get_state()
+    assert _eq(prev, g["prev_limit"])
+    assert _eq(pos, g["pos_limit"]), np.abs(pos - g["pos_limit"]).max()
+
+
+@pytest.mark.parametrize("name", ["env_t1_s1337.npz", "env_t1_s1338.npz", "env_t2_s1337.npz", "env_t3_s1337.npz"])
+def test_f64_env_steps_vs_reference(name):
+    """The reference ClothEnv's own step() results, reproduced bit-for-bit through clothb200_step_host_f64."""
+    g = load_golden(name)
+    bc = _bc(1, torch.float64)
+    bc.set_rest(g["rest"])
+    bc.set_state(g["pos_reset"], g["prev_reset"], g["pin_reset"])
+    bc.measure(); _sync()
+    assert abs(bc.coverage[0].item() - float(g["start_coverage"])) < 1e-12
+    assert abs(bc.variance_inv[0].item() - float(g["start_variance_inv"])) <= 1e-12 * abs(float(g["start_variance_inv"]))
+    bc.prev_coverage.copy_(bc.coverage)
+    out = {k: np.zeros(1, dt) for k, dt in (("reward", np.float64), ("done", np.int32), ("coverage", np.float64),
+                                              ("variance_inv", np.float64), ("flags", np.int32), ("sim_steps", np.int32))}
+    out["obs"] = np.zeros((1, 1875), np.float64)
+    sim = 0
+    for t, a in enumerate(g["actions"]):
+        bc.step_host(a[None, :], out)
+        steps, sim_ref, cov, var_inv, tear, oob = g["infos"][t]
+        sim += int(out["sim_steps"][0])
+        assert sim == int(sim_ref)
+        pos, prev, pin, grabm = bc.get_state()
+        assert _eq(pos, g["pos_a%d" % t]), np.abs(pos - g["pos_a%d" % t]).max()
+        assert _eq(prev, g["prev_a%d" % t])
+        assert _eq(pin, g["pin_a%d" % t].astype(bool))
+        assert _eq(out["obs"][0].reshape(625, 3), g["pos_a%d" % t])
+        assert sorted(set(g["grabbed_a%d" % t].tolist())) == bc.grabbed_set(0).tolist()
+        assert bc.n_grabbed[0].item() == len(g["grabbed_a%d" % t])
+        assert abs(out["coverage"][0] - cov) < 1e-12
+        assert abs(out["variance_inv"][0] - var_inv) <= 1e-12 * abs(var_inv)
+        f = int(out["flags"][0])
+        L = _lib()
+        assert bool(f & L.FLAG_TEAR) == bool(tear) and bool(f & L.FLAG_OOB) == bool(oob)
+        assert bool(f & L.FLAG_NOGRAB) == (len(g["grabbed_a%d" % t]) == 0)
+        assert abs(out["reward"][0] - g["rewards"][t]) < 1e-11
+        assert bool(out["done"][0]) == bool(g["dones"][t])
+        assert bc.num_steps[0].item() == int(steps) and bc.num_sim_steps[0].item() == int(sim_ref)
+
+
+def test_f64_tear():
+    g = load_golden("tear.npz")
+    L = _lib()
+    from gym_cloth_b200.batched import BatchedCloth
+    P = L.default_params()
+    P.reduce_factor = float(g["reduce_factor"])
+    bc = BatchedCloth(P, 1, dtype=torch.float64)
+    bc.measure(); _sync(); bc.prev_coverage.copy_(bc.coverage)
+    out = {"sim_steps": np.zeros(1, np.int32), "flags": np.zeros(1, np.int32), "coverage": np.zeros(1), "reward": np.zeros(1),
+           "done": np.zeros(1, np.int32)}
+    bc.step_host(g["action"][None, :], out)
+    assert out["sim_steps"][0] == int(g["info"][1]) and (out["flags"][0] & L.FLAG_TEAR)
+    pos, prev, pin, grabm = bc.get_state()
+    assert _eq(pos, g["pos"]) and _eq(prev, g["prev"]) and _eq(pin, g["pin"].astype(bool))
+    assert sorted(np.repeat(np.arange(625), grabm).tolist()) == sorted(g["grabbed_after"].tolist())   # not released
+    assert abs(out["reward"][0] - float(g["reward"])) < 1e-11 and bool(out["done"][0]) == bool(g["done"])
+    # second action on the torn cloth: exactly one update (sticky flag), grabbed list keeps growing
+    bc.step_host(g["action2"][None, :], out)
+    assert out["sim_steps"][0] == 1
+    pos, prev, pin, grabm = bc.get_state()
+    assert _eq(pos, g["pos2"]) and _eq(prev, g["prev2"]) and _eq(pin, g["pin2"].astype(bool))
+    assert sorted(np.repeat(np.arange(625), grabm).tolist()) == sorted(g["grabbed_after2"].tolist())
+
+
+# ----------------------------------------------------------------------------------------------- f64: oracle, batch
+def _random_actions(rng, n):
+    a = rng.uniform(-1, 1, size=(n, 4))
+    a[::3, :2] = rng.uniform(-0.9, 0.9, size=(len(a[::3]), 2))   # mostly inside the cloth
+    return a
+
+
+def test_f64_batch_vs_oracle_two_actions():
+    """16 environments with different actions in one launch; every env must equal its own oracle run."""
+    n = 16
+    rng = np.random.RandomState(42)
+    bc = _bc(n, torch.float64)
+    oracles = [OracleCloth() for _ in range(n)]
+    bc.measure(); _sync(); bc.prev_coverage.copy_(bc.coverage)
+    for rnd in range(2):
+        acts = _random_actions(rng, n)
+        out = {"sim_steps": np.zeros(n, np.int32), "coverage": np.zeros(n), "flags": np.zeros(n, np.int32)}
+        bc.step_host(acts, out)
+        for e in range(n):
+            nupd, ng, ip = oracles[e].step_action(acts[e])
+            pos, prev, pin, _ = bc.get_state(e)
+            op, oq, opin = oracles[e].get_state()
+            assert out["sim_steps"][e] == nupd, (rnd, e)
+            assert _eq(pos, op) and _eq(prev, oq) and _eq(pin, opin.astype(bool)), (rnd, e, np.abs(pos - op).max())
+            assert abs(out["coverage"][e] - oracles[e].coverage()) < 1e-12
+            assert bool(out["flags"][e] & 2) == oracles[e].out_of_bounds()
+            assert bool(out["flags"][e] & 1) == oracles[e].tear
+
+
+def test_f64_device_decode_matches_host_when_pow_is_exact():
+    L = _lib()
+    t = load_golden("decode.npz")["table"]
+    acts = t[:, :4].copy()
+    exact = np.array([all(v ** 2 == v * v for v in row[2:4]) for row in acts.tolist()])
+    bc = _bc(len(acts), torch.float64)
+    dev = torch.from_numpy(acts).cuda()
+    L.check(L.lib().clothb200_decode_actions_f64(C.byref(bc.P), len(acts), C.c_void_p(dev.data_ptr()),
+                                                 C.c_void_p(bc.plans.data_ptr()), bc.stream))
+    _sync()
+    raw = bc.plans.cpu().numpy().tobytes()
+    plans = (L.Plan * len(acts)).from_buffer_copy(raw)
+    host = bc.decode_host(acts)
+    n_exact = 0
+    for i in range(len(acts)):
+        assert (host[i].gx, host[i].gy, host[i].dxr, host[i].dyr, host[i].iters_pull) == (t[i, 4], t[i, 5], t[i, 6], t[i, 7], int(t[i, 8]))
+        assert (plans[i].gx, plans[i].gy) == (host[i].gx, host[i].gy)
+        assert abs(plans[i].iters_pull - host[i].iters_pull) <= 1
+        if exact[i] and (host[i].dxr, host[i].dyr) == (plans[i].dxr, plans[i].dyr):
+            n_exact += 1
+        assert abs(plans[i].dxr - host[i].dxr) < 1e-17 and abs(plans[i].dyr - host[i].dyr) < 1e-17
+    assert n_exact > 0.95 * len(acts)
+
+
+# ----------------------------------------------------------------------------------------------- f32
+def test_f32_single_update_tolerance():
+    g = load_golden("phases.npz")
+    for exact_rest in (False, True):
+        bc = _bc(1, torch.float32, exact_rest=exact_rest)
+        bc.set_state(g["pos_0"], g["prev_0"], g["pin_0"], grabbed=g["grabbed"])
+        bc.adjust(0.0016, -0.0012, 0.0)
+        bc.update(1)
+        pos, prev, _, _ = bc.get_state()
+        assert np.abs(pos - g["pos_limit"]).max() <= 2e-6
+        assert np.abs(prev - g["prev_limit"]).max() <= 2e-6
+
+
+def test_f32_action_tolerance_vs_oracle():
+    n = 32
+    rng = np.random.RandomState(7)
+    bc = _bc(n, torch.float32)
+    acts = _random_actions(rng, n)
+    acts[:, 2:] *= 0.6
+    out = {"sim_steps": np.zeros(n, np.int32), "coverage": np.zeros(n), "flags": np.zeros(n, np.int32)}
+    bc.step_host(acts, out)
+    maxes, means, dcov = [], [], []
+    for e in range(n):
+        o = OracleCloth()
+        nupd, ng, ip = o.step_action(acts[e])
+        assert out["sim_steps"][e] == nupd
+        assert bc.n_grabbed[e].item() == ng
+        pos, prev, pin, _ = bc.get_state(e)
+        d = np.abs(pos - o.pos)
+        maxes.append(d.max()); means.append(d.mean()); dcov.append(abs(out["coverage"][e] - o.coverage()))
+        assert not (out["flags"][e] & 8)
+    print("f32 vs oracle after one action: max %.3e  mean %.3e  dcov %.3e" % (max(maxes), max(means), max(dcov)))
+    assert max(maxes) <= 2e-2 and max(means) <= 1e-3 and max(dcov) <= 5e-3
+
+
+def test_f32_device_actions_match_host_actions():
+    """clothb200_step_actions_f32 (device decode) against clothb200_step_host_f32 (host decode)."""
+    n = 8
+    rng = np.random.RandomState(3)
+    acts = _random_actions(rng, n).astype(np.float32)
+    a = _bc(n, torch.float32); b = _bc(n, torch.float32)
+    a.step_actions(torch.from_numpy(acts).cuda())
+    b.step_host(acts.astype(np.float64), {})
+    _sync()
+    assert torch.equal(a.sim_steps, b.sim_steps)
+    assert (a.pos - b.pos).abs().max().item() <= 2e-2
+    assert torch.equal(a.n_grabbed, b.n_grabbed)
+
+
+# ----------------------------------------------------------------------------------------------- properties at full size
+def test_full_size_properties_4096():
+    """BASELINE config 2 size (4096 cloths): properties that need no oracle.
+    - an action that grips nothing leaves the state untouched and reports NOGRAB / 0 substeps;
+    - identical (state, action) pairs give identical results wherever they sit in the batch;
+    - flat cloth: coverage == 1, variance_inv == 1000, no flags."""
+    n = 4096
+    bc = _bc(n, torch.float32)
+    bc.measure(); _sync()
+    assert torch.all(bc.coverage == 1.0) and torch.all(bc.variance_inv == 1000.0) and torch.all(bc.flags == 0)
+    rng = np.random.RandomState(0)
+    base = _random_actions(rng, 8).astype(np.float32)
+    acts = np.tile(base, (n // 8, 1))
+    acts[5::8, :2] = 1.0   # corner (1,1) of the flat cloth is gripped; move the 6th of every 8 outside instead
+    acts[5::8, 0] = -1.0; acts[5::8, 1] = -1.0
+    pos0 = bc.pos.clone()
+    bc.step_actions(torch.from_numpy(acts).cuda()); _sync()
+    ss = bc.sim_steps.cpu().numpy().reshape(-1, 8)
+    assert (ss == ss[0]).all()
+    p = bc.pos.view(n // 8, 8, 625, 4)
+    assert torch.equal(p, p[0:1].expand_as(p))
+    cov = bc.coverage.view(-1, 8)
+    assert torch.equal(cov, cov[0:1].expand_as(cov))
+    nograb = (bc.flags & 4) != 0
+    if nograb.any():
+        idx = torch.nonzero(nograb)[:, 0]
+        assert torch.equal(bc.pos[idx], pos0[idx]) and torch.all(bc.sim_steps[idx] == 0)
+    assert int((bc.sim_steps > 0).sum()) >= n // 2
