@@ -13,6 +13,7 @@
 
 namespace clothb200 {
 std::atomic<long long> g_launch_count{0};
+long long *g_prof_ptr = nullptr;
 static thread_local std::string g_cuda_err;
 void set_cuda_error(cudaError_t e, const char *where) {
     g_cuda_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -163,6 +164,7 @@ size_t clothb200_sizeof_params(void) { return sizeof(ClothB200Params); }
 size_t clothb200_sizeof_plan(void) { return sizeof(ClothB200Plan); }
 size_t clothb200_sizeof_step(void) { return sizeof(ClothB200Step); }
 int64_t clothb200_launch_count(void) { return (int64_t)g_launch_count.load(); }
+int clothb200_debug_set_profile(void *dev_int64_nenv_x16) { g_prof_ptr = (long long *)dev_int64_nenv_x16; return CLOTHB200_OK; }
 
 int clothb200_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int *smem_per_sm) {
     int dev = device;

@@ -82,6 +82,7 @@ template <typename T> struct StepArgs {
     int32_t *done;
     const double *iters_up_env;
     const int32_t *env_order;
+    long long *prof;             // optional [n_env][16] cycle / event counters (debug)
 };
 
 enum { KMODE_STEP = 0, KMODE_UPDATE = 1, KMODE_GRAB = 2, KMODE_MEASURE = 3 };
@@ -149,10 +150,15 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     uint32_t *ev;            // [ev_words] stretched-spring queue
     int *misc;               // [16] counters/flags: 0 total, 1 nwork, 2 tear, 3 bad, 4.. scratch
     const T *rest;           // rest table of this env (REST_TABLE)
+    long long pacc[16];      // thread 0: cycles per phase + event counters when profiling
+    long long plast;
+    bool prof_on;
 
     __device__ ClothCTA(const DevParams<T> &P_, unsigned char *smem, const T *rest_)
         : P(P_), W(WC ? WC : P_.W), H(WC ? WC : P_.H), N(WC ? WC * WC : P_.N), tid(threadIdx.x), lane(threadIdx.x & 31),
-          warp(threadIdx.x >> 5), rest(rest_) {
+          warp(threadIdx.x >> 5), rest(rest_), plast(0), prof_on(false) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) pacc[i] = 0;
         size_t o = 0;
         pos = reinterpret_cast<P4 *>(smem + o); o += sizeof(P4) * (size_t)N;
         prev = reinterpret_cast<P4 *>(smem + o); o += sizeof(P4) * (size_t)N;
@@ -486,6 +492,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             }
             if (s == 0x7fffffff) break;
             cursor = s + 1;
+            if (prof_on && tid == 0) pacc[12] += 1;
             const int q = s / 6, k = s - q * 6;
             const int a = q - koff(k);
             P4 Pa = pos[a], Pb = pos[q];
@@ -497,6 +504,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             if (!(l > (rst * T(1.1)))) continue;
             T d0 = (Pa.x - Pb.x) / l, d1 = (Pa.y - Pb.y) / l, d2 = (Pa.z - Pb.z) / l;
             T extra = l - rst * T(1.1);
+            if (prof_on && tid == 0) pacc[13] += 1;
             if (pa) {
                 Pb = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w);
             } else if (pb) {
@@ -542,20 +550,25 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         for (int j = lane; j < nw; j += 32) ev[j] = 0u;
     }
 
+    __device__ __forceinline__ void ptick(int k) {
+        if (prof_on && tid == 0) { const long long t = clock64(); pacc[k] += t - plast; plast = t; }
+    }
     // ---- one Cloth.update() (cloth.pyx:169-214), reference order ----
     __device__ void update_reference_order() {
-        hooke_verlet();            sync();
-        commit_and_hash();         sync();
-        alloc_buckets();           sync();
-        scatter_members();         sync();
-        order_members();           sync();
-        collide_snapshot();        sync();
-        collide_first_and_plane(); sync();
-        collide_replay();          sync();
-        limit_snapshot();          sync();
+        if (prof_on && tid == 0) plast = clock64();
+        hooke_verlet();            sync(); ptick(0);
+        commit_and_hash();         sync(); ptick(1);
+        alloc_buckets();           sync(); ptick(2);
+        scatter_members();         sync(); ptick(3);
+        order_members();           sync(); ptick(4);
+        collide_snapshot();        sync(); ptick(5);
+        collide_first_and_plane(); sync(); ptick(6);
+        if (prof_on && tid == 0) pacc[11] += misc[1];
+        collide_replay();          sync(); ptick(7);
+        limit_snapshot();          sync(); ptick(8);
         limit_replay();
         if (tid == 0) { misc[0] = 0; misc[1] = 0; }
-        sync();
+        sync(); ptick(9);
     }
 
     // ---- Gripper (gripper.pyx) ----

@@ -9,6 +9,7 @@
 namespace clothb200 {
 
 extern std::atomic<long long> g_launch_count;   // defined in cloth_abi.cu
+extern long long *g_prof_ptr;                    // debug: per-env phase counters (clothb200_debug_set_profile)
 void set_cuda_error(cudaError_t e, const char *where);
 
 // ------------------------------------------------------------------------------------------------
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     const int tid = threadIdx.x;
     const T *rest_env = REST_TABLE ? A.rest + (long long)env * A.rest_env_stride : nullptr;
     CTA c(P, smem, rest_env);
+    c.prof_on = A.prof != nullptr;
     const int N = c.N;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + CTA::smem_bytes(N, P.table_size, P.ev_words) - 16);
     const uint32_t bytes = (uint32_t)(sizeof(P4) * (size_t)N);
@@ -129,6 +131,10 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
             A.reward[env] = rew;
             A.done[env] = (steps >= P.max_actions) || tear || oob || (cov > 0.92);
         }
+    }
+    if (A.prof && tid == 0) {
+        c.pacc[10] = nupd;
+        for (int i = 0; i < 16; i++) A.prof[(size_t)env * 16 + i] = c.pacc[i];
     }
     (void)iters_pull;
 }

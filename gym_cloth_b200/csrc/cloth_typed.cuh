@@ -20,6 +20,7 @@ template <typename T> StepArgs<T> make_args(int n_env, const ClothB200Step *io) 
         }
         A.iters_up_env = io->iters_up_env; A.env_order = io->env_order;
     }
+    A.prof = g_prof_ptr;
     return A;
 }
 

@@ -1,0 +1,527 @@
+"""Host-side mirror of gym_cloth/envs/cloth_env.py for the B200 path.
+
+`BatchedClothEnv`  n independent ClothEnv instances on one GPU (vector-env API).
+`ClothEnv`         single-env facade with the reference's constructor, method and attribute names
+                   (cloth_env.py:55-1228), so that scripts such as examples/analytic.py keep working.
+
+All arithmetic of the hot path (Cloth.update, Gripper, the substep loop, coverage/reward/terminal)
+runs in libclothb200.so; this file holds only what the reference also does in Python: config handling,
+random draws for resets and the gym-style bookkeeping.  Random numbers are drawn from
+np.random.RandomState streams in exactly the order the reference draws them, environment i using
+seed + i, so environment i replays the reference ClothEnv seeded with seed + i (bit-exactly in f64).
+"""
+import copy
+import pickle
+
+import numpy as np
+import torch
+import yaml
+
+from .. import lib as _l
+from ..batched import BatchedCloth
+
+_REWARD_THRESHOLDS = {"coverage": 0.92, "coverage-delta": 0.92}   # cloth_env.py:42-50 (coverage types only)
+
+
+def load_cfg(cfg):
+    if isinstance(cfg, dict):
+        return copy.deepcopy(cfg)
+    with open(cfg, "r") as fh:
+        return yaml.safe_load(fh)
+
+
+class _Box(object):
+    """The two attributes of gym.spaces.Box that ClothEnv users touch (cloth_env.py:148-181)."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype); self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape; self.dtype = np.dtype(dtype)
+        self.np_random = np.random.RandomState()
+
+    def seed(self, seed=None):
+        self.np_random = np.random.RandomState(seed); return [seed]
+
+    def sample(self):
+        return self.np_random.uniform(self.low, self.high, size=self.shape).astype(self.dtype)
+
+
+def _randval_minabs(rs, low, high, minabs=None):   # cloth_env.py:825-833
+    val = rs.uniform(low=low, high=high)
+    if minabs is not None:
+        while np.abs(val) < minabs:
+            val = rs.uniform(low=low, high=high)
+    return val
+
+
+def _prevent_oob(val, dval, lower=0.0, upper=1.0):   # cloth_env.py:835-841
+    if val + dval < lower:
+        dval = lower - val
+    elif val + dval > upper:
+        dval = upper - val
+    return dval
+
+
+class BatchedClothEnv(object):
+    """n_env ClothEnv instances stepped by one kernel launch per env.step.
+
+    actions: [n_env, 4] in env.step's format (cfg clip_act_space/delta_actions as in cfg/t*_rgbd.yaml).
+    Global environment ids are env_offset + i (multi-GPU shards pass their offset) and only seed the RNG
+    streams, so results do not depend on how the batch is sharded.
+    """
+
+    def __init__(self, cfg, n_env, dtype="f32", device=None, seed=None, env_offset=0, dom_rand_draws=False):
+        self.cfg = load_cfg(cfg)
+        cfg = self.cfg
+        self.P = _l.params_from_cfg(cfg)
+        env = cfg["env"]
+        if env["obs_type"] != "1d":
+            raise ValueError(env["obs_type"])            # only the 1-D observation is on the hot path
+        self.reward_type = env["reward_type"]
+        assert "coverage" in self.reward_type             # cloth_env.py:130
+        if self.reward_type != "coverage-delta":
+            raise NotImplementedError(self.reward_type)
+        if not (env["clip_act_space"] and env["delta_actions"]):
+            raise NotImplementedError("reset actions need delta_actions (cloth_env.py:861-862)")
+        self.init_type = cfg["init"]["type"]
+        self.n_env = int(n_env)
+        self.env_offset = int(env_offset)
+        self.torch_dtype = torch.float32 if dtype in ("f32", torch.float32) else torch.float64
+        self.max_actions = env["max_actions"]
+        self.grip_radius = env["grip_radius"]
+        self.dom_rand_draws = dom_rand_draws
+        self.N = self.P.num_width_points * self.P.num_height_points
+        self.action_space = _Box([-1., -1., -1., -1.], [1., 1., 1., 1.])
+        lim = 100
+        self.observation_space = _Box(-lim * np.ones(3 * self.N), lim * np.ones(3 * self.N))
+        self.cloth = BatchedCloth(self.P, self.n_env, dtype=self.torch_dtype, device=device,
+                                  init_type="tier1" if self.init_type == "tier3" else self.init_type,
+                                  noise=np.zeros(self.N) if self.init_type == "tier2" else None)
+        self.device = self.cloth.device
+        self.init_side = np.ones(self.n_env, bool)
+        self.start_coverage = torch.zeros(self.n_env, dtype=torch.float64, device=self.device)
+        self.start_variance_inv = torch.zeros(self.n_env, dtype=torch.float64, device=self.device)
+        self._pinned = None
+        self.seed(cfg.get("seed", 0) if seed is None else seed)
+
+    # ------------------------------------------------------------------ seeding
+    def seed(self, seed=None):
+        """Environment i draws from np.random.RandomState(seed + env_offset + i) (cloth_env.py:332-341)."""
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy % (2 ** 31))
+        self._seed = int(seed)
+        self.rngs = [np.random.RandomState((self._seed + self.env_offset + i) % (2 ** 32)) for i in range(self.n_env)]
+        return [seed]
+
+    # ------------------------------------------------------------------ helpers
+    def _sel(self, envs):
+        if envs is None:
+            return np.arange(self.n_env)
+        return np.asarray(envs, np.int64).reshape(-1)
+
+    def _points_xy(self, envs, pidx):
+        """(x, y) of point pidx[j] of environment envs[j] as Python-exact doubles."""
+        e = torch.as_tensor(envs, device=self.device); p = torch.as_tensor(pidx, device=self.device)
+        return self.cloth.pos[e, p, :2].double().cpu().numpy()
+
+    def _step_subset(self, envs, actions, initialize, iters_up=None):
+        """step(action, initialize) for a subset of environments (host decode = CPython arithmetic)."""
+        c = self.cloth
+        full = np.zeros((self.n_env, 4))
+        full[envs] = actions
+        plans = c.decode_host(full)
+        order = torch.as_tensor(envs, dtype=torch.int32, device=self.device)
+        old_order, old_n, old_iu = c.env_order, c.n_env, c.iters_up_env
+        if iters_up is not None:
+            iu = np.full(self.n_env, float(self.P.iters_up)); iu[envs] = iters_up
+            c.iters_up_env = torch.from_numpy(iu).to(self.device)
+        host = torch.frombuffer(bytearray(bytes(plans)), dtype=torch.uint8).reshape(self.n_env, -1)
+        c.plans.copy_(host)
+        c.env_order, c.n_env = order, len(envs)
+        try:
+            c.step_plans(c.plans, initialize=initialize)
+        finally:
+            c.env_order, c.n_env, c.iters_up_env = old_order, old_n, old_iu
+
+    def _update_subset(self, envs, n_updates):
+        c = self.cloth
+        order = torch.as_tensor(envs, dtype=torch.int32, device=self.device)
+        old_order, old_n = c.env_order, c.n_env
+        c.env_order, c.n_env = order, len(envs)
+        try:
+            c.update(n_updates)
+        finally:
+            c.env_order, c.n_env = old_order, old_n
+
+    def _measure_subset(self, envs):
+        c = self.cloth
+        order = torch.as_tensor(envs, dtype=torch.int32, device=self.device)
+        old_order, old_n = c.env_order, c.n_env
+        c.env_order, c.n_env = order, len(envs)
+        try:
+            c.measure()
+        finally:
+            c.env_order, c.n_env = old_order, old_n
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ reset (cloth_env.py:717-987)
+    def reset(self, envs=None):
+        """Start a new episode in the given environments (all by default).  Returns obs [n_env, 3N]."""
+        envs = self._sel(envs)
+        c = self.cloth
+        n = len(envs)
+        if n == 0:
+            return c.obs
+        # Cloth.__init__ (cloth.pyx:75, 94-130): init_side is always drawn, tier2 draws the x-noise
+        sides = np.array([self.rngs[e].rand() > 0.5 for e in envs])
+        self.init_side[envs] = sides
+        if self.init_type == "tier2":
+            noise = np.stack([self.rngs[e].rand(self.N) * 0.01 - 0.005 for e in envs])
+            c.reset_grid("tier2", noise=noise, init_side=sides, envs=envs)
+        else:
+            c.reset_grid("tier1", envs=envs)
+        idx_t = torch.as_tensor(envs, device=self.device)
+        c.num_steps[idx_t] = 0; c.num_sim_steps[idx_t] = 0
+        self.init_actions = {int(e): [] for e in envs}
+        self._reset_actions(envs, sides)
+        self._measure_subset(envs)
+        self.start_coverage[idx_t] = c.coverage[idx_t]
+        self.start_variance_inv[idx_t] = c.variance_inv[idx_t]
+        c.prev_coverage[idx_t] = c.coverage[idx_t]
+        if self.dom_rand_draws:
+            # cloth_env.py:786-789 consumes np_random draws for image noise the 1-D observation never uses;
+            # replayed so that later resets of the same stream see the reference's numbers (App. B-1: _wd=_hd=224)
+            for e in envs:
+                rs = self.rngs[e]
+                rs.uniform(low=40, high=50); rs.uniform(low=0.7, high=1.3)
+                lim = rs.uniform(low=-15.0, high=15.0)
+                rs.uniform(low=-lim, high=lim, size=(224, 224, 3))
+        return c.obs
+
+    def _clip_space(self, x, y, dx, dy):   # _convert_action_to_clip_space, cloth_env.py:1207-1215
+        return ((x - 0.5) * 2, (y - 0.5) * 2, dx, dy)
+
+    def _reset_actions(self, envs, sides):
+        c = self.cloth
+        n = len(envs)
+        if self.init_type == "tier1":      # cloth_env.py:843-891
+            lim = 0.20
+
+            def pull(sub):
+                pidx = np.array([self.rngs[e].randint(self.N) for e in sub])
+                draws = [(_randval_minabs(self.rngs[e], -lim, lim, 0.08), _randval_minabs(self.rngs[e], -lim, lim, 0.08)) for e in sub]
+                xy = self._points_xy(sub, pidx)
+                acts = np.zeros((len(sub), 4))
+                for j, e in enumerate(sub):
+                    px, py = float(xy[j, 0]), float(xy[j, 1])
+                    dx = _prevent_oob(px, draws[j][0]); dy = _prevent_oob(py, draws[j][1])
+                    acts[j] = self._clip_space(px, py, dx, dy)
+                    self.init_actions[int(e)].append(acts[j].copy())
+                self._step_subset(sub, acts, initialize=True)
+
+            pull(envs); pull(envs)
+            self._measure_subset(envs)
+            cov = c.coverage[torch.as_tensor(envs, device=self.device)].cpu().numpy()
+            third = envs[cov >= 0.90]
+            if len(third):
+                pull(third)
+        elif self.init_type == "tier2":    # cloth_env.py:893-949
+            self._update_subset(envs, 1500)
+            init_side = np.where(sides, 1, -1)
+            corner = np.array([-25 if self.rngs[e].rand() < 0.5 else -1 for e in envs])
+            W = self.P.num_width_points
+            pidx = np.where(corner == -25, self.N - W, self.N - 1)
+            dx0 = np.array([self.rngs[e].uniform(0.30, 0.50) for e in envs]) * init_side
+            dy0 = np.array([self.rngs[e].uniform(0.30, 0.60) if corner[j] == -25 else self.rngs[e].uniform(-0.60, -0.30)
+                            for j, e in enumerate(envs)])
+            xy = self._points_xy(envs, pidx)
+            acts = np.array([self._clip_space(float(xy[j, 0]), float(xy[j, 1]), dx0[j], dy0[j]) for j in range(n)])
+            for j, e in enumerate(envs):
+                self.init_actions[int(e)].append(acts[j].copy())
+            self._step_subset(envs, acts, initialize=True)
+            pidx = np.where(corner == -25, self.N - 19, self.N - 7)
+            dx1 = np.array([self.rngs[e].uniform(0.30, 0.60) for e in envs]) * init_side
+            dy1 = np.array([self.rngs[e].uniform(-0.30, -0.60) if corner[j] == -25 else self.rngs[e].uniform(0.30, 0.60)
+                            for j, e in enumerate(envs)])
+            xy = self._points_xy(envs, pidx)
+            acts = np.array([self._clip_space(float(xy[j, 0]), float(xy[j, 1]), dx1[j], dy1[j]) for j in range(n)])
+            for j, e in enumerate(envs):
+                self.init_actions[int(e)].append(acts[j].copy())
+            self._step_subset(envs, acts, initialize=True)
+            self._update_subset(envs, 500)
+        elif self.init_type == "tier3":    # cloth_env.py:951-982
+            iters_up = np.array([self.rngs[e].uniform(low=200, high=280) for e in envs])
+            lim = 0.25
+            acts = np.zeros((n, 4))
+            for j, e in enumerate(envs):
+                rs = self.rngs[e]
+                p0x = _randval_minabs(rs, 0.30, 0.70); p0y = _randval_minabs(rs, 0.30, 0.70)
+                dx0 = _randval_minabs(rs, -lim, lim, 0.10); dy0 = _randval_minabs(rs, -lim, lim, 0.10)
+                dx0 = _prevent_oob(p0x, dx0); dy0 = _prevent_oob(p0y, dy0)
+                acts[j] = self._clip_space(p0x, p0y, dx0, dy0)
+                self.init_actions[int(e)].append(acts[j].copy())
+            self.reset_iters_up = iters_up
+            self._step_subset(envs, acts, initialize=True, iters_up=iters_up)
+            self._update_subset(envs, 800)
+        else:
+            raise ValueError(self.init_type)
+
+    # ------------------------------------------------------------------ step (cloth_env.py:369-534)
+    def step(self, actions, host_out=None):
+        """One env.step for every environment.
+
+        actions: np.ndarray / sequence [n_env, 4]  -> host decode (bit-exact with CPython), host results
+                 torch CUDA tensor [n_env, 4]      -> device decode, results stay on the device
+        Returns (obs, reward, done, info) with info = dict of per-env arrays (cloth_env.py:524-533)."""
+        c = self.cloth
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            c.step_actions(actions.to(self.torch_dtype).contiguous())
+            obs, rew, done = c.obs, c.reward, c.done
+            info = self._info(c.coverage, c.variance_inv, c.flags, c.num_steps, c.num_sim_steps)
+            return obs, rew, done, info
+        a = np.asarray(actions, np.float64).reshape(self.n_env, 4)
+        out = host_out if host_out is not None else self.host_buffers()
+        c.step_host(a, out)
+        info = self._info(out["coverage"], out["variance_inv"], out["flags"], None, None)
+        info["sim_steps"] = out["sim_steps"]
+        return out["obs"], out["reward"], out["done"], info
+
+    def host_buffers(self):
+        """Pinned host arrays for step(): reused across calls."""
+        if getattr(self, "_host", None) is None:
+            n = self.n_env
+            npdt = torch.float32 if self.torch_dtype == torch.float32 else torch.float64
+            pin = lambda *s, dt: torch.zeros(*s, dtype=dt).pin_memory()
+            t = {"obs": pin(n, 3 * self.N, dt=npdt), "reward": pin(n, dt=torch.float64), "done": pin(n, dt=torch.int32),
+                 "coverage": pin(n, dt=torch.float64), "variance_inv": pin(n, dt=torch.float64),
+                 "flags": pin(n, dt=torch.int32), "sim_steps": pin(n, dt=torch.int32)}
+            self._host_t = t
+            self._host = {k: v.numpy() for k, v in t.items()}
+        return self._host
+
+    def _info(self, coverage, variance_inv, flags, num_steps, num_sim_steps):
+        return {"actual_coverage": coverage, "variance_inv": variance_inv,
+                "have_tear": (flags & _l.FLAG_TEAR) != 0, "out_of_bounds": (flags & _l.FLAG_OOB) != 0,
+                "no_grab": (flags & _l.FLAG_NOGRAB) != 0, "bad_state": (flags & _l.FLAG_BADSTATE) != 0,
+                "num_steps": num_steps if num_steps is not None else self.cloth.num_steps,
+                "num_sim_steps": num_sim_steps if num_sim_steps is not None else self.cloth.num_sim_steps,
+                "start_coverage": self.start_coverage, "start_variance_inv": self.start_variance_inv}
+
+    def get_random_action(self, atype="over_xy_plane"):   # cloth_env.py:989-1018
+        if atype == "over_xy_plane":
+            return np.stack([self.action_space.sample() for _ in range(self.n_env)])
+        raise ValueError(atype)
+
+    # ------------------------------------------------------------------ state pool (fast synthetic resets)
+    def snapshot(self):
+        c = self.cloth
+        return {"pos": c.pos.clone(), "prev": c.prev.clone(), "cov": c.coverage.clone(),
+                "rest": None if c.rest is None else c.rest.clone()}
+
+    def reset_from_pool(self, pool, envs, choice):
+        """Copy pool states choice[j] into environments envs[j] (device-side, no physics)."""
+        c = self.cloth
+        e = torch.as_tensor(envs, device=self.device); k = torch.as_tensor(choice, device=self.device)
+        c.pos[e] = pool["pos"][k]; c.prev[e] = pool["prev"][k]
+        c.prev_coverage[e] = pool["cov"][k]
+        self.start_coverage[e] = pool["cov"][k]
+        c.flags[e] = 0; c.num_steps[e] = 0; c.num_sim_steps[e] = 0
+
+
+class _PointView(object):
+    """Read/write view of one point of the facade's host copy (point.pyx:17-58 attribute names)."""
+    __slots__ = ("_c", "_i")
+
+    def __init__(self, cloth, i):
+        self._c, self._i = cloth, i
+
+    x = property(lambda s: float(s._c._host()[0][s._i, 0]))
+    y = property(lambda s: float(s._c._host()[0][s._i, 1]))
+    z = property(lambda s: float(s._c._host()[0][s._i, 2]))
+    px = property(lambda s: float(s._c._host()[1][s._i, 0]))
+    py = property(lambda s: float(s._c._host()[1][s._i, 1]))
+    pz = property(lambda s: float(s._c._host()[1][s._i, 2]))
+    pinned = property(lambda s: bool(s._c._host()[2][s._i]))
+    orig_x = property(lambda s: float(s._c._orig[s._i, 0]))
+    orig_y = property(lambda s: float(s._c._orig[s._i, 1]))
+    orig_z = property(lambda s: float(s._c._orig[s._i, 2]))
+    identity_0 = property(lambda s: float(s._i // s._c.width))
+    identity_1 = property(lambda s: float(s._i % s._c.width))
+
+    def __repr__(self):
+        return "({:.3f}, {:.3f}, {:.3f})".format(self.x, self.y, self.z)
+
+
+class _ClothFacade(object):
+    """`env.cloth`: the names of gym_cloth.physics.cloth.Cloth that callers use (cloth.pyx:390-408, analytic.py:105-125)."""
+
+    def __init__(self, benv):
+        self._b = benv
+        self.params = benv.cfg
+        self.width = benv.P.num_width_points; self.height = benv.P.num_height_points
+        self.bounds = (1, 1, 1)
+        self._cache = None
+        self._orig = None
+        self.pts = [_PointView(self, i) for i in range(benv.N)]
+
+    def _invalidate(self):
+        self._cache = None
+
+    def _host(self):
+        if self._cache is None:
+            pos, prev, pin, _ = self._b.cloth.get_state(0)
+            self._cache = (pos, prev, pin)
+        return self._cache
+
+    @property
+    def init_side(self):
+        return bool(self._b.init_side[0])
+
+    @property
+    def have_tear(self):
+        return bool(self._b.cloth.flags[0].item() & _l.FLAG_TEAR)
+
+    @property
+    def allpts_arr(self):
+        return self._host()[0].copy()
+
+    @property
+    def pinnedpts_arr(self):
+        pos, _, pin = self._host()
+        return pos[pin]
+
+    def update(self):
+        self._b.cloth.update(1); self._invalidate()
+
+
+class _GripperFacade(object):
+    """`env.gripper`: gym_cloth.physics.gripper.Gripper (gripper.pyx)."""
+
+    def __init__(self, benv, cloth):
+        self._b, self.cloth = benv, cloth
+        self.grip_radius = benv.grip_radius
+
+    @property
+    def grabbed_pts(self):
+        m = self._b.cloth.get_state(0)[3]
+        return [self.cloth.pts[i] for i in np.repeat(np.arange(len(m)), m)]
+
+    def grab_top(self, x, y):
+        self._b.cloth.grab_top((x, y), self.grip_radius); self.cloth._invalidate()
+
+    def adjust(self, x, y, z):
+        self._b.cloth.adjust(x, y, z); self.cloth._invalidate()
+
+    def release(self):
+        self._b.cloth.release(); self.cloth._invalidate()
+
+
+class ClothEnv(object):
+    """Drop-in for gym_cloth.envs.ClothEnv on the hot path: same constructor, reset/step/seed/state and the
+    attributes scripts read (cloth_env.py:58-186, 332-534, 717-796).  dtype='f64' reproduces the reference
+    bit for bit; 'f32' is the production precision."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, cfg_file, subrank=None, start_state_path=None, dtype="f64", device=None):
+        self.cfg_file = cfg_file
+        self._b = BatchedClothEnv(cfg_file, 1, dtype=dtype, device=device, dom_rand_draws=True)
+        self.cfg = self._b.cfg
+        env = self.cfg["env"]
+        for k in ("max_actions", "iters_up", "iters_up_rest", "iters_pull_max", "iters_grip_rest", "iters_rest",
+                  "reduce_factor", "grip_radius"):
+            setattr(self, k, env[k])
+        self.reward_type = env["reward_type"]
+        self.bounds = (1, 1, 1)
+        self.render_proc = None
+        self._logger_idx = subrank
+        self._occlusion_vec = [True, True, True, True]
+        self.num_w = self._b.P.num_width_points; self.num_h = self._b.P.num_height_points
+        self.num_points = self._b.N
+        self.action_space = self._b.action_space
+        self.observation_space = self._b.observation_space
+        self._start_state = None
+        if start_state_path is not None:
+            with open(start_state_path, "rb") as fh:
+                self._start_state = pickle.load(fh)
+        self.cloth = _ClothFacade(self._b)
+        self.gripper = _GripperFacade(self._b, self.cloth)
+        self.num_steps = 0; self.num_sim_steps = 0; self.have_tear = False
+        self._current_coverage = 0.0
+        self.seed()
+
+    # the reference reads these from the env, keep them live
+    @property
+    def np_random(self):
+        return self._b.rngs[0]
+
+    def seed(self, seed=None):
+        return self._b.seed(seed)
+
+    @property
+    def state(self):                       # cloth_env.py:188-200
+        return self.cloth.allpts_arr.reshape(-1)
+
+    def _sync_counters(self):
+        c = self._b.cloth
+        self.num_steps = int(c.num_steps[0].item()); self.num_sim_steps = int(c.num_sim_steps[0].item())
+        self.have_tear = bool(c.flags[0].item() & _l.FLAG_TEAR)
+
+    def reset(self):
+        b = self._b
+        if self._start_state is not None:
+            st = self._start_state
+            b.rngs[0].rand()               # Cloth.__init__ still draws init_side (cloth.pyx:75)
+            b.cloth.set_state(st["pos"], st["prev"], st.get("pinned"))
+            if "rest" in st:
+                b.cloth.set_rest(st["rest"])
+            b.cloth.num_steps.zero_(); b.cloth.num_sim_steps.zero_()
+            b._measure_subset(np.arange(1))
+            b.cloth.prev_coverage.copy_(b.cloth.coverage)
+            b.start_coverage.copy_(b.cloth.coverage); b.start_variance_inv.copy_(b.cloth.variance_inv)
+        else:
+            b.reset()
+        self.cloth._invalidate()
+        self.cloth._orig = self.cloth.allpts_arr if self.cloth._orig is None else self.cloth._orig
+        self._sync_counters()
+        self._start_coverage = float(b.start_coverage[0].item())
+        self._start_variance_inv = float(b.start_variance_inv[0].item())
+        self._prev_reward = self._start_coverage
+        return self.state
+
+    def step(self, action, initialize=False):
+        b = self._b
+        a = np.array([float(v) for v in action], np.float64).reshape(1, 4)
+        if initialize:
+            b._step_subset(np.arange(1), a, initialize=True)
+            self.cloth._invalidate()
+            return None
+        obs, rew, done, info = b.step(a)
+        self.cloth._invalidate()
+        self._sync_counters()
+        self._current_coverage = float(info["actual_coverage"][0])
+        self._prev_reward = self._current_coverage
+        out_info = {"num_steps": self.num_steps, "num_sim_steps": self.num_sim_steps,
+                    "actual_coverage": self._current_coverage, "start_coverage": self._start_coverage,
+                    "variance_inv": float(info["variance_inv"][0]), "start_variance_inv": self._start_variance_inv,
+                    "have_tear": self.have_tear, "out_of_bounds": bool(info["out_of_bounds"][0])}
+        return np.array(obs[0], np.float64), float(rew[0]), bool(done[0]), out_info
+
+    def _compute_coverage(self):
+        self._b._measure_subset(np.arange(1)); return float(self._b.cloth.coverage[0].item())
+
+    def _compute_variance(self):
+        self._b._measure_subset(np.arange(1)); return float(self._b.cloth.variance_inv[0].item())
+
+    def _out_of_bounds(self):
+        self._b._measure_subset(np.arange(1)); return bool(self._b.cloth.flags[0].item() & _l.FLAG_OOB)
+
+    def get_random_action(self, atype="over_xy_plane"):
+        return self._b.get_random_action(atype)[0]
+
+    def save_state(self, cloth_file):
+        """Like cloth_env.py:343-350, but arrays instead of pickled Point objects."""
+        pos, prev, pin, _ = self._b.cloth.get_state(0)
+        with open(cloth_file, "wb") as fh:
+            pickle.dump({"pos": pos, "prev": prev, "pinned": pin}, fh)
+
+    def render(self, filepath, mode="human", close=False):
+        pass   # the OpenGL viewer is a display-only side channel

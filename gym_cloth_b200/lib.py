@@ -74,6 +74,7 @@ _PROTOS = {
     "clothb200_bench_smem_bandwidth": (_i, [_i, C.POINTER(_d), _vp]),
     "clothb200_bench_fp32_flops": (_i, [_i, C.POINTER(_d), _vp]),
     "clothb200_launch_count": (_i64, []),
+    "clothb200_debug_set_profile": (_i, [_vp]),
 }
 _TYPED = {
     "clothb200_init_grid": (_i, [_PP, _i, _vp, _i, _vp, _vp, _vp]),

@@ -197,6 +197,9 @@ int clothb200_bench_smem_bandwidth(int iters, double *gb_per_s, void *stream);
 int clothb200_bench_fp32_flops(int iters, double *tflop_per_s, void *stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t clothb200_launch_count(void);
+/* debug: DEVICE int64 [n_env][16]; when set, the step kernel records per-phase SM cycles of thread 0 and event counts
+ * (0..9 phases of Cloth.update, 10 substeps, 11 replayed buckets, 12 limit-queue pops, 13 springs shortened). NULL = off. */
+int clothb200_debug_set_profile(void *dev_int64_nenv_x16);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,123 @@
+"""Drive the reference's own compiled physics (oracle/_ref) through one ClothEnv.step (TEST/BASELINE
+INFRASTRUCTURE; used by bench.py's cpu_baseline / --impl reference legs and by tests only).
+
+gym_cloth/envs/cloth_env.py is pure Python and lives only in /root/reference, which does not exist on
+the GPU box, so the ~40 lines of its step loop (cloth_env.py:401-515) are restated here around the
+reference's real `Cloth.update()` / `Gripper` objects, which is where > 99 % of the time goes
+(SURVEY.md §3.3).  tests/test_ref_driver.py checks this driver against fixtures recorded from the
+reference ClothEnv itself.
+"""
+import math
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+_CFG = {"cloth": {"num_width_points": 25, "num_height_points": 25, "width": 1, "height": 1, "density": 200.0,
+                  "ks": 10000.0, "damping": 2.0, "thickness": 0.02, "plane_friction": 1.0, "tear_thresh": 2.0,
+                  "pin_cond": "y=0", "color_pts": "None"},
+        "frames_per_sec": 30, "simulation_steps": 30, "seed": 1, "init": {"type": "tier1"}}
+_ENV = {"iters_up": 50, "iters_up_rest": 80, "iters_grip_rest": 300, "iters_rest": 1000, "reduce_factor": 0.002,
+        "grip_radius": 0.003}
+
+
+def make_ref_cloth(pos=None, prev=None, rest=None):
+    """A reference Cloth + Gripper pair, optionally loaded with a given state."""
+    from oracle.ref_loader import load_physics
+    Cloth, Gripper, _ = load_physics()
+    c = Cloth(params=_CFG, render=False, random_state=np.random.RandomState(0))
+    if pos is not None:
+        for p, x, q in zip(c.pts, np.asarray(pos, np.float64).tolist(), np.asarray(prev, np.float64).tolist()):
+            p.x, p.y, p.z = x
+            p.px, p.py, p.pz = q
+    if rest is not None:
+        for s, r in zip(c.springs, np.asarray(rest, np.float64).tolist()):
+            s.rest_length = r
+    g = Gripper(c, _ENV["grip_radius"], _CFG["cloth"]["height"], _CFG["cloth"]["thickness"])
+    return c, g
+
+
+def ref_step(c, g, action):
+    """cloth_env.py:401-515 (clip_act_space, delta_actions) on reference objects. Returns #updates."""
+    x, y, dx, dy = (max(min(float(v), 1.0), -1.0) for v in action)
+    x = (x / 2.0) + 0.5
+    y = (y / 2.0) + 0.5
+    g.grab_top(x, y)
+    total = np.sqrt(dx ** 2 + dy ** 2)
+    xr = dx / (total + 1e-5) * _ENV["reduce_factor"]
+    yr = dy / (total + 1e-5) * _ENV["reduce_factor"]
+    ii, cur = 0, 0
+    while True:
+        cur += np.sqrt(xr ** 2 + yr ** 2)
+        if cur >= total:
+            break
+        ii += 1
+    iu, iur, igr, ir = _ENV["iters_up"], _ENV["iters_up_rest"], _ENV["iters_grip_rest"], _ENV["iters_rest"]
+    iterations = iu + iur + ii + igr + ir
+    if len(g.grabbed_pts) == 0:
+        iterations = 0
+    i = 0
+    n = 0
+    while i < iterations:
+        if i < iu:
+            g.adjust(x=0.0, y=0.0, z=0.0025)
+        elif i < iu + iur:
+            pass
+        elif i < iu + iur + ii:
+            g.adjust(x=xr, y=yr, z=0.0)
+        elif i < iu + iur + ii + igr:
+            pass
+        else:
+            g.release()
+        c.update()
+        n += 1
+        if c.have_tear:
+            break
+        i += 1
+    return n
+
+
+def ref_coverage(c):
+    from scipy.spatial import ConvexHull
+    pts = np.array([[min(max(p.x, 0), 1), min(max(p.y, 0), 1)] for p in c.pts])
+    try:
+        return ConvexHull(pts).volume
+    except Exception:
+        return 0
+
+
+def _worker(args):
+    kind, pos, prev, action = args
+    t0 = time.perf_counter()
+    if kind == "reference":
+        c, g = make_ref_cloth(pos, prev)
+        n = ref_step(c, g, action)
+        cov = ref_coverage(c)
+    else:
+        from oracle.oracle import OracleCloth
+        o = OracleCloth()
+        o.set_state(pos, prev, np.zeros(len(pos), np.uint8))
+        n, _, _ = o.step_action(np.asarray(action, np.float64))
+        cov = o.coverage()
+    return n, cov, time.perf_counter() - t0
+
+
+def cpu_env_steps(kind, states, actions, cores=None):
+    """Run len(actions) env.step calls on `cores` host processes (one ClothEnv each, like the reference's
+    'one CPU per analytic.py process' model, analysis/README.md:9-11).  states: list of (pos, prev).
+    Returns dict(value env-steps/s, substeps/s, seconds, cores, n)."""
+    cores = cores or os.cpu_count() or 1
+    jobs = [(kind, s[0], s[1], a) for s, a in zip(states, actions)]
+    cores = max(1, min(cores, len(jobs)))
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_worker(j) for j in jobs]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_worker, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    sub = sum(r[0] for r in res)
+    return {"value": len(jobs) / dt, "substeps_per_s": sub / dt, "seconds": dt, "cores": cores, "n": len(jobs),
+            "substeps": sub, "coverage": [r[1] for r in res]}
