@@ -52,7 +52,9 @@ template <typename T> struct DevParams {
     T kk_struct, kk_bend;        // ks*1.0, ks*0.2 (cloth.pyx:225-232)
     T dsdm, damp;                // (dt*dt)/mass, 1-damping/100 (cloth.pyx:240-241)
     T cell_w, cell_h, cell_t;    // 3dx, 3dy, max (cloth.pyx:308-310)
-    T thresh;                    // 2*thickness (cloth.pyx:317)
+    T inv_cell_w, inv_cell_h, inv_cell_t;
+    int cell_pow2;               // cell sizes are powers of two: x/w == x*(1/w) exactly
+    T thresh, thresh2;           // 2*thickness (cloth.pyx:317) and its square
     T sim_steps;                 // simulation_steps as scalar (cloth.pyx:338-340)
     T min_z, fric1, surf_off;    // minimum_z, 1-plane_friction, 1e-4 (cloth.pyx:345-370)
     T tear_thresh;
@@ -138,6 +140,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     typedef typename V4<T>::type P4;
     static constexpr int NWARPS = NT / 32;
+    static constexpr bool FAST = (sizeof(T) == 4);   // f32 production math; the f64 build evaluates the reference's expressions
 
     const DevParams<T> &P;
     const int W, H, N;
@@ -150,15 +153,14 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     uint32_t *ev;            // [ev_words] stretched-spring queue
     int *misc;               // [16] counters/flags: 0 total, 1 nwork, 2 tear, 3 bad, 4.. scratch
     const T *rest;           // rest table of this env (REST_TABLE)
-    long long pacc[16];      // thread 0: cycles per phase + event counters when profiling
+    int rot;                 // blockIdx-derived rotation of the warp roles (spreads serial phases over the 4 SM sub-partitions)
+    long long *pacc;         // [16] smem: thread 0's cycles per phase + event counters when profiling
     long long plast;
     bool prof_on;
 
     __device__ ClothCTA(const DevParams<T> &P_, unsigned char *smem, const T *rest_)
         : P(P_), W(WC ? WC : P_.W), H(WC ? WC : P_.H), N(WC ? WC * WC : P_.N), tid(threadIdx.x), lane(threadIdx.x & 31),
-          warp(threadIdx.x >> 5), rest(rest_), plast(0), prof_on(false) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) pacc[i] = 0;
+          warp(threadIdx.x >> 5), rest(rest_), rot((int)blockIdx.x), plast(0), prof_on(false) {
         size_t o = 0;
         pos = reinterpret_cast<P4 *>(smem + o); o += sizeof(P4) * (size_t)N;
         prev = reinterpret_cast<P4 *>(smem + o); o += sizeof(P4) * (size_t)N;
@@ -166,12 +168,13 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         tinfo = reinterpret_cast<uint32_t *>(smem + o); o += 4 * (size_t)P.table_size;
         ev = reinterpret_cast<uint32_t *>(smem + o); o += 4 * (size_t)((P.ev_words + 3) & ~3);
         misc = reinterpret_cast<int *>(smem + o); o += 4 * 16;
+        pacc = reinterpret_cast<long long *>(smem + o); o += 8 * 16;
         pslot = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
         lstA = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
         lstB = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
     }
     static __host__ __device__ size_t smem_bytes(int N, int table_size, int ev_words) {
-        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 4 * (size_t)((ev_words + 3) & ~3) + 64 +
+        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 4 * (size_t)((ev_words + 3) & ~3) + 64 + 128 +
                3 * 2 * (size_t)((N + 7) & ~7) + 16 /* mbarrier */;
     }
 
@@ -180,89 +183,122 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     }
 
     // ---- spring topology (cloth.pyx:135-146).  Spring slot s = q*6 + k: k-th spring created by point q. ----
-    // offset from q back to ptA for kind k
-    __device__ __forceinline__ int koff(int k) const {
-        switch (k) {
-            case 0: return W;      // STRUCTURAL (r-1,c)
-            case 1: return 1;      // STRUCTURAL (r,c-1)
-            case 2: return W + 1;  // SHEARING   (r-1,c-1)
-            case 3: return W - 1;  // SHEARING   (r-1,c+1)
-            case 4: return 2 * W;  // BENDING    (r-2,c)
-            default: return 2;     // BENDING    (r,c-2)
-        }
+    // All helpers are branch-free (no jump tables): they sit on the critical path of the serial replays.
+    // offset from q back to ptA for kind k: {W, 1, W+1, W-1, 2W, 2} packed 10 bits each
+    __device__ __forceinline__ unsigned long long koff_pack() const {
+        return (unsigned long long)W | (1ull << 10) | ((unsigned long long)(W + 1) << 20) | ((unsigned long long)(W - 1) << 30) |
+               ((unsigned long long)(2 * W) << 40) | (2ull << 50);
     }
-    // does point (r,c) create spring kind k?
-    __device__ __forceinline__ bool kvalid(int r, int c, int k) const {
-        switch (k) {
-            case 0: return r > 0;
-            case 1: return c > 0;
-            case 2: return r > 0 && c > 0;
-            case 3: return r > 0 && c + 1 < W;
-            case 4: return r > 1;
-            default: return c > 1;
-        }
+    __device__ __forceinline__ int koff(int k) const { return (int)((koff_pack() >> (10 * k)) & 1023ull); }
+    // bit k set <=> point (r,c) creates spring kind k
+    __device__ __forceinline__ unsigned vmask(int r, int c) const {
+        const unsigned r0 = r > 0, c0 = c > 0, cw = c + 1 < W, r1 = r > 1, c1 = c > 1;
+        return r0 | (c0 << 1) | ((r0 & c0) << 2) | ((r0 & cw) << 3) | (r1 << 4) | (c1 << 5);
+    }
+    __device__ __forceinline__ bool kvalid(int r, int c, int k) const { return (vmask(r, c) >> k) & 1u; }
+    // per-kind constant selected with compares (k is usually warp-uniform); avoids register-indexed constant loads
+    __device__ __forceinline__ T sel6(const T *v, int k) const {
+        T lo = k == 0 ? v[0] : (k == 1 ? v[1] : v[2]);
+        T hi = k == 3 ? v[3] : (k == 4 ? v[4] : v[5]);
+        return k < 3 ? lo : hi;
     }
     __device__ __forceinline__ T rest_of(int q, int k) const {
         if (REST_TABLE) return __ldg(rest + q * 6 + k);
-        return P.rest_k[k];
+        return sel6(P.rest_k, k);
     }
     __device__ __forceinline__ T kk_of(int k) const { return k >= 4 ? P.kk_bend : P.kk_struct; }
 
-    // ---- Hooke (cloth.pyx:221-237) gathered per point + Verlet (cloth.pyx:239-256) ----
-    // The new position is parked in prev[p].xyz (prev is private to the owner thread); commit_verlet()
-    // swaps it in after the barrier, when no thread reads old positions any more.
-    __device__ __forceinline__ void spring_force(const P4 &Pa, const P4 &Pb, T kk, T rst, T &f0, T &f1, T &f2) {
-        // l2_norm_ab = fastnorm(pb-pa); force_mg = ks*kc*(l-rest)/l; force_on_a = force_mg*(pb-pa)
-        T d0 = Pb.x - Pa.x, d1 = Pb.y - Pa.y, d2 = Pb.z - Pa.z;
-        T l = norm3(d0, d1, d2);
-        if (l == T(0)) { misc[3] = 1; f0 = f1 = f2 = T(0); return; }  // reference: ZeroDivisionError
-        T fm = kk * (l - rst) / l;
-        f0 = fm * d0; f1 = fm * d1; f2 = fm * d2;
+    // ---- distance predicates ----
+    // f32 build: squared-distance forms (no sqrt).  f64 build: the reference's exact `fastnorm(...) <op> c`
+    // decision; a squared-distance pre-filter with a 1e-15 relative guard band decides all but razor-edge
+    // cases without the sqrt, the remaining ones evaluate the reference expression itself.
+    // true <=> fastnorm(d) > c   (c = rest*1.1 or rest*tear_thresh, as the reference computes it)
+    __device__ __forceinline__ bool longer_than(T d0, T d1, T d2, T c) const {
+        const T q = d0 * d0 + d1 * d1 + d2 * d2;
+        const T c2 = c * c;
+        if (FAST) return q > c2;
+        if (q > c2 * T(1.000000000000001)) return true;
+        if (q < c2 * T(0.999999999999999)) return false;
+        return sqrt_t(q) > c;
+    }
+    // true <=> fastnorm(d) <= thresh  (cloth.pyx:330)
+    __device__ __forceinline__ bool within_thresh(T q) const {
+        if (FAST) return q <= P.thresh2;
+        if (q < P.thresh2 * T(0.999999999999999)) return true;
+        if (q > P.thresh2 * T(1.000000000000001)) return false;
+        return sqrt_t(q) <= P.thresh;
     }
 
-    __device__ void hooke_verlet() {
+    // ---- Hooke (cloth.pyx:221-237) gathered per point + Verlet (cloth.pyx:239-256) ----
+    // One spring's contribution to point p, selected without branches so that the 12 neighbour loads and
+    // the 12 independent force evaluations of a point can overlap.  SIGN=+1: p is ptA, -1: p is ptB.
+    template <int SIGN>
+    __device__ __forceinline__ void add_spring(bool valid, const P4 &Pa, const P4 &Pb, T kk, T rst, T &fx, T &fy, T &fz, int &bad) {
+        const T d0 = Pb.x - Pa.x, d1 = Pb.y - Pa.y, d2 = Pb.z - Pa.z;
+        const T q = d0 * d0 + d1 * d1 + d2 * d2;
+        T fm;
+        if (FAST) {
+            fm = kk - (kk * rst) * rsqrtf((float)q);          // ks*kc*(l-rest)/l
+        } else {
+            const T l = sqrt_t(q);                               // fastnorm
+            fm = kk * (l - rst) / l;
+        }
+        bad |= (valid && q == T(0)) ? 1 : 0;                     // reference: ZeroDivisionError
+        const T f0 = fm * d0, f1 = fm * d1, f2 = fm * d2;
+        if (SIGN > 0) { fx = valid ? fx + f0 : fx; fy = valid ? fy + f1 : fy; fz = valid ? fz + f2 : fz; }
+        else { fx = valid ? fx + (-f0) : fx; fy = valid ? fy + (-f1) : fy; fz = valid ? fz + (-f2) : fz; }
+    }
+
+    // The new position is parked in prev[p].xyz (prev is private to the owner thread); commit_and_hash()
+    // swaps it in after the barrier, when no thread reads old positions any more.
+    __device__ __forceinline__ void hooke_verlet() {
+        int bad = 0;
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];
             if (Pp.w != T(0)) continue;  // pinned: Verlet skips it, its force is never used
             const int r = p / W, c = p - r * W;
+            const bool v0 = r > 0, v1 = c > 0, v2 = v0 && v1, v3 = v0 && (c + 1 < W), v4 = r > 1, v5 = c > 1;
+            const bool u0 = c + 1 < W, u1 = c + 2 < W, dn = r + 1 < H, u2 = dn && v1, u3 = dn, u4 = dn && u0, u5 = r + 2 < H;
+            // all twelve neighbours first (invalid ones alias p itself: in range, result discarded)
+            const P4 A0 = pos[v0 ? p - W : p], A1 = pos[v1 ? p - 1 : p], A2 = pos[v2 ? p - W - 1 : p];
+            const P4 A3 = pos[v3 ? p - W + 1 : p], A4 = pos[v4 ? p - 2 * W : p], A5 = pos[v5 ? p - 2 : p];
+            const P4 B0 = pos[u0 ? p + 1 : p], B1 = pos[u1 ? p + 2 : p], B2 = pos[u2 ? p + W - 1 : p];
+            const P4 B3 = pos[u3 ? p + W : p], B4 = pos[u4 ? p + W + 1 : p], B5 = pos[u5 ? p + 2 * W : p];
+            const P4 Q = prev[p];
             // _reset_gravity: f = 0 then f += (0,0,mg)
             T fx = T(0) + T(0), fy = T(0) + T(0), fz = T(0) + P.mg;
-            T a0, a1, a2;
-            // springs created by p (p is ptB): ptB.add_force(-F)
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (kvalid(r, c, k)) {
-                    const int a = p - koff(k);
-                    spring_force(pos[a], Pp, kk_of(k), rest_of(p, k), a0, a1, a2);
-                    fx = fx + (-a0); fy = fy + (-a1); fz = fz + (-a2);
-                }
-            }
+            // springs created by p (p is ptB, ptB.add_force(-F)), creation order k = 0..5
+            add_spring<-1>(v0, A0, Pp, P.kk_struct, rest_of(p, 0), fx, fy, fz, bad);
+            add_spring<-1>(v1, A1, Pp, P.kk_struct, rest_of(p, 1), fx, fy, fz, bad);
+            add_spring<-1>(v2, A2, Pp, P.kk_struct, rest_of(p, 2), fx, fy, fz, bad);
+            add_spring<-1>(v3, A3, Pp, P.kk_struct, rest_of(p, 3), fx, fy, fz, bad);
+            add_spring<-1>(v4, A4, Pp, P.kk_bend, rest_of(p, 4), fx, fy, fz, bad);
+            add_spring<-1>(v5, A5, Pp, P.kk_bend, rest_of(p, 5), fx, fy, fz, bad);
             // springs created by later points in which p is ptA, in creation order:
             // q = p+1 (k=1), p+2 (k=5), p+W-1 (k=3), p+W (k=0), p+W+1 (k=2), p+2W (k=4)
-            if (c + 1 < W) { spring_force(Pp, pos[p + 1], P.kk_struct, rest_of(p + 1, 1), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
-            if (c + 2 < W) { spring_force(Pp, pos[p + 2], P.kk_bend, rest_of(p + 2, 5), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
-            if (r + 1 < H) {
-                if (c > 0) { spring_force(Pp, pos[p + W - 1], P.kk_struct, rest_of(p + W - 1, 3), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
-                { spring_force(Pp, pos[p + W], P.kk_struct, rest_of(p + W, 0), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
-                if (c + 1 < W) { spring_force(Pp, pos[p + W + 1], P.kk_struct, rest_of(p + W + 1, 2), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
-            }
-            if (r + 2 < H) { spring_force(Pp, pos[p + 2 * W], P.kk_bend, rest_of(p + 2 * W, 4), a0, a1, a2); fx = fx + a0; fy = fy + a1; fz = fz + a2; }
+            add_spring<1>(u0, Pp, B0, P.kk_struct, rest_of(u0 ? p + 1 : p, 1), fx, fy, fz, bad);
+            add_spring<1>(u1, Pp, B1, P.kk_bend, rest_of(u1 ? p + 2 : p, 5), fx, fy, fz, bad);
+            add_spring<1>(u2, Pp, B2, P.kk_struct, rest_of(u2 ? p + W - 1 : p, 3), fx, fy, fz, bad);
+            add_spring<1>(u3, Pp, B3, P.kk_struct, rest_of(u3 ? p + W : p, 0), fx, fy, fz, bad);
+            add_spring<1>(u4, Pp, B4, P.kk_struct, rest_of(u4 ? p + W + 1 : p, 2), fx, fy, fz, bad);
+            add_spring<1>(u5, Pp, B5, P.kk_bend, rest_of(u5 ? p + 2 * W : p, 4), fx, fy, fz, bad);
             // Verlet: new = x + damp*(x-px) + f*dsdm
-            const P4 Q = prev[p];
             T nx = Pp.x + (P.damp * (Pp.x - Q.x)) + (fx * P.dsdm);
             T ny = Pp.y + (P.damp * (Pp.y - Q.y)) + (fy * P.dsdm);
             T nz = Pp.z + (P.damp * (Pp.z - Q.z)) + (fz * P.dsdm);
             prev[p] = mk4(nx, ny, nz, Q.w);
         }
+        if (bad) misc[3] = 1;
     }
 
     // ---- commit Verlet + build_spatial_map pass 1 (cloth.pyx:298-311): find/insert bucket, count ----
-    __device__ __forceinline__ int cell(T v, T w) {
-        T f = floor_t(v / w);
+    __device__ __forceinline__ int cell(T v, T w, T inv_w) {
+        // floor(v / w); when w is a power of two the product with 1/w is the same number
+        T f = floor_t(P.cell_pow2 ? v * inv_w : v / w);
         if (!(f > T(-1048576) && f < T(1048576))) { misc[3] = 1; f = T(0); }  // NaN/huge: reference raises
         return (int)f;
     }
-    __device__ void commit_and_hash() {
+    __device__ __forceinline__ void commit_and_hash() {
         for (int p = tid; p < N; p += NT) {
             P4 Pp = pos[p];
             if (Pp.w == T(0)) {
@@ -271,7 +307,8 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                 Pp = mk4(Nw.x, Nw.y, Nw.z, T(0));
                 pos[p] = Pp;
             }
-            const int key = 961 * cell(Pp.x, P.cell_w) + 31 * cell(Pp.y, P.cell_h) + cell(Pp.z, P.cell_t);
+            const int key = 961 * cell(Pp.x, P.cell_w, P.inv_cell_w) + 31 * cell(Pp.y, P.cell_h, P.inv_cell_h) +
+                            cell(Pp.z, P.cell_t, P.inv_cell_t);
             uint32_t slot = ((uint32_t)key * 2654435761u) >> P.table_shift;
             const uint32_t msk = (uint32_t)P.table_size - 1;
             for (;;) {
@@ -288,7 +325,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         }
     }
     // pass 2: the first arriver of each bucket reserves its range in the member list
-    __device__ void alloc_buckets() {
+    __device__ __forceinline__ void alloc_buckets() {
         for (int p = tid; p < N; p += NT) {
             const uint32_t s = pslot[p];
             if (s & 0x8000u) {
@@ -301,7 +338,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         }
     }
     // pass 3: unordered scatter (high half of tinfo runs from off to off+cnt)
-    __device__ void scatter_members() {
+    __device__ __forceinline__ void scatter_members() {
         for (int p = tid; p < N; p += NT) {
             const uint32_t slot = pslot[p] & 0x7fffu;
             const uint32_t idx = atomicAdd(&tinfo[slot], 0x10000u) >> 16;
@@ -309,7 +346,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         }
     }
     // pass 4: rank inside the bucket -> index-ordered list (the dict value order of cloth.pyx:301-305)
-    __device__ void order_members() {
+    __device__ __forceinline__ void order_members() {
         for (int p = tid; p < N; p += NT) {
             const uint32_t info = tinfo[pslot[p] & 0x7fffu];
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
@@ -327,11 +364,13 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             const int q = lstB[start + j];
             if (q == p) continue;
             const P4 Pq = pos[q];
-            T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-            T d = norm3(d0, d1, d2);
-            if (d <= P.thresh) {
-                if (d == T(0)) { misc[3] = 1; continue; }
-                T factor = (P.thresh - d) / d;
+            const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+            const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+            if (within_thresh(qq)) {
+                if (qq == T(0)) { misc[3] = 1; continue; }
+                T factor;
+                if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);     // (thresh-d)/d
+                else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
                 t0 += d0 * factor; t1 += d1 * factor; t2 += d2 * factor;
                 n += 1;
             }
@@ -343,7 +382,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         return n;
     }
     // snapshot evaluation of every point: only records, per bucket, the first point that has a hit
-    __device__ void collide_snapshot() {
+    __device__ __forceinline__ void collide_snapshot() {
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];
             if (Pp.w != T(0)) continue;
@@ -351,8 +390,27 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             const uint32_t info = tinfo[slot];
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
             if (cnt < 2) continue;
-            T cx, cy, cz;
-            if (collide_point(p, Pp, start, cnt, cx, cy, cz)) atomicMin(&tkey[slot], p);
+            bool hit = false;
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {       // four candidates in flight
+                const int q0 = lstB[start + j], q1 = lstB[start + j + 1], q2 = lstB[start + j + 2], q3 = lstB[start + j + 3];
+                const P4 Q0 = pos[q0], Q1 = pos[q1], Q2 = pos[q2], Q3 = pos[q3];
+                const T a0 = Pp.x - Q0.x, a1 = Pp.y - Q0.y, a2 = Pp.z - Q0.z;
+                const T b0 = Pp.x - Q1.x, b1 = Pp.y - Q1.y, b2 = Pp.z - Q1.z;
+                const T c0 = Pp.x - Q2.x, c1 = Pp.y - Q2.y, c2 = Pp.z - Q2.z;
+                const T e0 = Pp.x - Q3.x, e1 = Pp.y - Q3.y, e2 = Pp.z - Q3.z;
+                hit |= (q0 != p) && within_thresh(a0 * a0 + a1 * a1 + a2 * a2);
+                hit |= (q1 != p) && within_thresh(b0 * b0 + b1 * b1 + b2 * b2);
+                hit |= (q2 != p) && within_thresh(c0 * c0 + c1 * c1 + c2 * c2);
+                hit |= (q3 != p) && within_thresh(e0 * e0 + e1 * e1 + e2 * e2);
+            }
+            for (; j < cnt; j++) {
+                const int q0 = lstB[start + j];
+                const P4 Q0 = pos[q0];
+                const T a0 = Pp.x - Q0.x, a1 = Pp.y - Q0.y, a2 = Pp.z - Q0.z;
+                hit |= (q0 != p) && within_thresh(a0 * a0 + a1 * a1 + a2 * a2);
+            }
+            if (hit) atomicMin(&tkey[slot], p);
         }
     }
     // _handle_plane_collision (cloth.pyx:345-370)
@@ -368,30 +426,29 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     }
     // first hit points take their snapshot correction and queue their bucket for the ordered replay;
     // points of buckets without any hit are final and get their plane collision here.
-    __device__ void collide_first_and_plane() {
+    __device__ __forceinline__ void collide_first_and_plane() {
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];
             if (Pp.w != T(0)) continue;
             const uint32_t slot = pslot[p] & 0x7fffu;
-            const uint32_t info = tinfo[slot];
-            const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
             const int first = tkey[slot];
             // A bucket with a hit is finished by collide_replay(): its members must keep their
             // pre-plane positions while the first hit point re-reads them below.
-            const bool replay = (first != CLOTH_FIRST_NONE);
+            if (first == CLOTH_FIRST_NONE) { plane_point(p); continue; }
             if (first == p) {
+                const uint32_t info = tinfo[slot];
+                const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
                 T cx, cy, cz;
                 if (collide_point(p, Pp, start, cnt, cx, cy, cz)) pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
                 lstA[atomicAdd(&misc[1], 1)] = (uint16_t)slot;
             }
-            if (!replay) plane_point(p);
         }
     }
     // ordered replay of one bucket by one warp: points after the first hit, in index order;
     // lanes evaluate candidates, contributions are summed in candidate order.
-    __device__ void collide_replay() {
+    __device__ __forceinline__ void collide_replay() {
         const int nwork = misc[1];
-        for (int wi = warp; wi < nwork; wi += NWARPS) {
+        for (int wi = (warp + NWARPS - rot % NWARPS) % NWARPS; wi < nwork; wi += NWARPS) {
             const uint32_t slot = lstA[wi];
             const uint32_t info = tinfo[slot];
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
@@ -402,69 +459,129 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                 const unsigned m = __ballot_sync(0xffffffffu, j < cnt && lstB[start + j] == first);
                 if (m) { j0 = base + __ffs(m) - 1; break; }
             }
-            for (int j = j0 + 1; j < cnt; j++) {
-                const int p = lstB[start + j];
-                const P4 Pp = pos[p];
-                if (Pp.w != T(0)) continue;
-                T t0 = T(0), t1 = T(0), t2 = T(0);
-                int n = 0;
-                for (int base = 0; base < cnt; base += 32) {
-                    const int cj = base + lane;
-                    const bool valid = cj < cnt && cj != j;
+            if (cnt <= 32) {
+                // common case: the whole bucket fits the warp; every lane keeps its member's index, positions
+                // are re-read after each update (only one member moves per step)
+                const int mine = lane < cnt ? lstB[start + lane] : 0;
+                for (int j = j0 + 1; j < cnt; j++) {
+                    const int p = __shfl_sync(0xffffffffu, mine, j);
+                    const P4 Pp = pos[p];
+                    if (Pp.w != T(0)) continue;
                     T c0 = T(0), c1 = T(0), c2 = T(0);
                     bool hit = false;
-                    if (valid) {
-                        const P4 Pq = pos[lstB[start + cj]];
-                        T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-                        T d = norm3(d0, d1, d2);
-                        if (d <= P.thresh) {
-                            if (d == T(0)) misc[3] = 1;
+                    if (lane < cnt && lane != j) {
+                        const P4 Pq = pos[mine];
+                        const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+                        const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                        if (within_thresh(qq)) {
+                            if (qq == T(0)) misc[3] = 1;
                             else {
-                                T factor = (P.thresh - d) / d;
+                                T factor;
+                                if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                                else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
                                 c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
                                 hit = true;
                             }
                         }
                     }
                     unsigned m = __ballot_sync(0xffffffffu, hit);
-                    n += __popc(m);
-                    while (m) {
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        t0 += __shfl_sync(0xffffffffu, c0, l);
-                        t1 += __shfl_sync(0xffffffffu, c1, l);
-                        t2 += __shfl_sync(0xffffffffu, c2, l);
+                    if (m) {
+                        const int n = __popc(m);
+                        T t0 = T(0), t1 = T(0), t2 = T(0);
+                        while (m) {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1;
+                            t0 += __shfl_sync(0xffffffffu, c0, l);
+                            t1 += __shfl_sync(0xffffffffu, c1, l);
+                            t2 += __shfl_sync(0xffffffffu, c2, l);
+                        }
+                        if (lane == 0) {
+                            const T nf = (T)n;
+                            const T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
+                            pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
+                        }
+                        __syncwarp();
                     }
                 }
-                if (n && lane == 0) {
-                    T nf = (T)n;
-                    T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
-                    pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
-                }
                 __syncwarp();
+                if (lane < cnt) plane_point(mine);
+            } else {
+                for (int j = j0 + 1; j < cnt; j++) {
+                    const int p = lstB[start + j];
+                    const P4 Pp = pos[p];
+                    if (Pp.w != T(0)) continue;
+                    T t0 = T(0), t1 = T(0), t2 = T(0);
+                    int n = 0;
+                    for (int base = 0; base < cnt; base += 32) {
+                        const int cj = base + lane;
+                        const bool valid = cj < cnt && cj != j;
+                        T c0 = T(0), c1 = T(0), c2 = T(0);
+                        bool hit = false;
+                        if (valid) {
+                            const P4 Pq = pos[lstB[start + cj]];
+                            const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+                            const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                            if (within_thresh(qq)) {
+                                if (qq == T(0)) misc[3] = 1;
+                                else {
+                                    T factor;
+                                    if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                                    else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                                    c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
+                                    hit = true;
+                                }
+                            }
+                        }
+                        unsigned m = __ballot_sync(0xffffffffu, hit);
+                        n += __popc(m);
+                        while (m) {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1;
+                            t0 += __shfl_sync(0xffffffffu, c0, l);
+                            t1 += __shfl_sync(0xffffffffu, c1, l);
+                            t2 += __shfl_sync(0xffffffffu, c2, l);
+                        }
+                    }
+                    if (n && lane == 0) {
+                        const T nf = (T)n;
+                        const T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
+                        pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
+                    }
+                    __syncwarp();
+                }
+                for (int base = 0; base < cnt; base += 32)
+                    if (base + lane < cnt) plane_point(lstB[start + base + lane]);
             }
-            for (int base = 0; base < cnt; base += 32)
-                if (base + lane < cnt) plane_point(lstB[start + base + lane]);
             __syncwarp();
         }
     }
 
     // ---- _limit_spring_changes (cloth.pyx:258-296) ----
-    __device__ __forceinline__ bool spring_flagged(const P4 &Pa, const P4 &Pb, T rst) {
+    // c_min = min(rest*1.1, rest*tear_thresh): a spring longer than that needs the sequential treatment
+    __device__ __forceinline__ T limit_c(T rst) const {
+        const T a = rst * T(1.1), b = rst * P.tear_thresh;
+        return a < b ? a : b;
+    }
+    __device__ __forceinline__ bool spring_flagged(const P4 &Pa, const P4 &Pb, T rst) const {
         if (Pa.w != T(0) && Pb.w != T(0)) return false;
-        T l = norm3(Pa.x - Pb.x, Pa.y - Pb.y, Pa.z - Pb.z);
-        return (l > rst * P.tear_thresh) || (l > (rst * T(1.1)));
+        return longer_than(Pa.x - Pb.x, Pa.y - Pb.y, Pa.z - Pb.z, limit_c(rst));
     }
     // snapshot test of all springs; also clears the hash table for the next substep
-    __device__ void limit_snapshot() {
+    __device__ __forceinline__ void limit_snapshot() {
         for (int j = tid; j < P.table_size; j += NT) { tkey[j] = CLOTH_KEY_EMPTY; tinfo[j] = 0u; }
         for (int p = tid; p < N; p += NT) {
             const P4 Pb = pos[p];
             const int r = p / W, c = p - r * W;
+            const bool v0 = r > 0, v1 = c > 0, v2 = v0 && v1, v3 = v0 && (c + 1 < W), v4 = r > 1, v5 = c > 1;
+            const P4 A0 = pos[v0 ? p - W : p], A1 = pos[v1 ? p - 1 : p], A2 = pos[v2 ? p - W - 1 : p];
+            const P4 A3 = pos[v3 ? p - W + 1 : p], A4 = pos[v4 ? p - 2 * W : p], A5 = pos[v5 ? p - 2 : p];
             uint32_t bits = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-                if (kvalid(r, c, k) && spring_flagged(pos[p - koff(k)], Pb, rest_of(p, k))) bits |= 1u << k;
+            bits |= (v0 && spring_flagged(A0, Pb, rest_of(p, 0))) ? 1u : 0u;
+            bits |= (v1 && spring_flagged(A1, Pb, rest_of(p, 1))) ? 2u : 0u;
+            bits |= (v2 && spring_flagged(A2, Pb, rest_of(p, 2))) ? 4u : 0u;
+            bits |= (v3 && spring_flagged(A3, Pb, rest_of(p, 3))) ? 8u : 0u;
+            bits |= (v4 && spring_flagged(A4, Pb, rest_of(p, 4))) ? 16u : 0u;
+            bits |= (v5 && spring_flagged(A5, Pb, rest_of(p, 5))) ? 32u : 0u;
             if (bits) {
                 const int s = p * 6;
                 const int sh = s & 31;
@@ -474,77 +591,109 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             }
         }
     }
-    // ordered replay by warp 0 (all lanes execute the spring update redundantly, lane 0 stores)
-    __device__ void limit_replay() {
-        if (warp != 0) return;
+    // lowest flagged slot >= from (warp-wide, all lanes get the result); 0x7fffffff if none
+    __device__ __forceinline__ int next_flagged(int from) const {
         const int nw = P.ev_words;
-        int cursor = 0;
-        for (;;) {
-            // pop the lowest flagged spring slot >= cursor
-            int s = 0x7fffffff;
-            for (int base = cursor >> 5; base < nw; base += 32) {
-                const int wi = base + lane;
-                uint32_t word = wi < nw ? ev[wi] : 0u;
-                if (wi == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
-                const int cand = word ? (wi << 5) + __ffs(word) - 1 : 0x7fffffff;
-                s = __reduce_min_sync(0xffffffffu, cand);
-                if (s != 0x7fffffff) break;
-            }
-            if (s == 0x7fffffff) break;
-            cursor = s + 1;
-            if (prof_on && tid == 0) pacc[12] += 1;
-            const int q = s / 6, k = s - q * 6;
-            const int a = q - koff(k);
+        for (int base = from >> 5; base < nw; base += 32) {
+            const int wi = base + lane;
+            uint32_t word = wi < nw ? ev[wi] : 0u;
+            if (wi == (from >> 5)) word &= ~((1u << (from & 31)) - 1u);
+            const int cand = word ? (wi << 5) + __ffs(word) - 1 : 0x7fffffff;
+            const int s = __reduce_min_sync(0xffffffffu, cand);
+            if (s != 0x7fffffff) return s;
+        }
+        return 0x7fffffff;
+    }
+    // Ordered replay by one warp.  Every lane evaluates the popped spring redundantly (no broadcast needed);
+    // lanes 0-23 additionally own one of the <= 2 x 12 springs incident to its end points (a fixed per-lane
+    // geometry) and re-test it in registers against the updated end point, so that the next pop is
+    // min(already flagged, newly flagged) without a round trip through shared memory.
+    __device__ __forceinline__ void limit_replay(int replay_warp) {
+        if (warp != replay_warp) return;
+        // per-lane incident spring: i in 0..11 relative to end point x (lanes 0-11: ptA, 12-23: ptB of the event)
+        const int i = lane < 12 ? lane : lane - 12;
+        // springs 0..5 are created by x itself (x is ptB); 6..11 by x+1, x+2, x+W-1, x+W, x+W+1, x+2W with x as ptA
+        const int inc_dq = i < 6 ? 0 : (i == 6 ? 1 : (i == 7 ? 2 : (i == 8 ? W - 1 : (i == 9 ? W : (i == 10 ? W + 1 : 2 * W)))));
+        const int inc_k = i < 6 ? i : (i == 6 ? 1 : (i == 7 ? 5 : (i == 8 ? 3 : (i == 9 ? 0 : (i == 10 ? 2 : 4)))));
+        const int inc_other = i < 6 ? -koff(inc_k) : inc_dq;   // the end point that is not x, relative to x
+        const bool lane_active = lane < 24;
+        const T rst_lane = REST_TABLE ? T(0) : sel6(P.rest_k, inc_k);
+        const unsigned long long kp = koff_pack();
+        const int nw = P.ev_words;
+        int s = next_flagged(0);
+        while (s != 0x7fffffff) {
+            const int q = (int)(((unsigned)s * 43691u) >> 18);   // s / 6 for s < 2^17
+            const int k = s - q * 6;
+            const int a = q - (int)((kp >> (10 * k)) & 1023ull);
+            // flags already queued beyond s: loaded now, consumed at the end of the iteration
+            const int wi0 = (s + 1) >> 5;
+            uint32_t word = (wi0 + lane < nw) ? ev[wi0 + lane] : 0u;
+            if (lane == 0) word &= ~((1u << ((s + 1) & 31)) - 1u);
             P4 Pa = pos[a], Pb = pos[q];
+            // my incident spring
+            const int x = lane < 12 ? a : q;
+            const int qq = x + inc_dq;
+            const int s2 = qq * 6 + inc_k;
+            const int r2 = qq / W, c2 = qq - r2 * W;
+            const bool inc_ok = lane_active && qq < N && s2 > s && ((vmask(r2, c2) >> inc_k) & 1u);
+            const P4 Po = pos[inc_ok ? x + inc_other : x];
+            const T rst2 = REST_TABLE ? __ldg(rest + (inc_ok ? s2 : s)) : rst_lane;
+            const T rst = REST_TABLE ? __ldg(rest + s) : sel6(P.rest_k, k);
+            if (prof_on && tid == replay_warp * 32) pacc[12] += 1;
             const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
-            if (pa && pb) continue;
-            const T rst = rest_of(q, k);
-            T l = norm3(Pa.x - Pb.x, Pa.y - Pb.y, Pa.z - Pb.z);
-            if (l > rst * P.tear_thresh) misc[2] = 1;
-            if (!(l > (rst * T(1.1)))) continue;
-            T d0 = (Pa.x - Pb.x) / l, d1 = (Pa.y - Pb.y) / l, d2 = (Pa.z - Pb.z) / l;
-            T extra = l - rst * T(1.1);
-            if (prof_on && tid == 0) pacc[13] += 1;
-            if (pa) {
-                Pb = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w);
-            } else if (pb) {
-                Pa = mk4(Pa.x - d0 * extra, Pa.y - d1 * extra, Pa.z - d2 * extra, Pa.w);
-            } else {
-                T ed = extra * T(0.5);
-                Pa = mk4(Pa.x - d0 * ed, Pa.y - d1 * ed, Pa.z - d2 * ed, Pa.w);
-                Pb = mk4(Pb.x + d0 * ed, Pb.y + d1 * ed, Pb.z + d2 * ed, Pb.w);
-            }
-            if (lane == 0) { if (!pa) pos[a] = Pa; if (!pb) pos[q] = Pb; }
-            __syncwarp();
-            // re-test the later springs incident to the moved points: lanes 0-11 -> a, 12-23 -> q
-            if (lane < 24) {
-                const int x = lane < 12 ? a : q;
-                const bool moved = lane < 12 ? !pa : !pb;
-                const int i = lane < 12 ? lane : lane - 12;
-                int qq, kk;
-                if (i < 6) { qq = x; kk = i; }
-                else {
-                    // springs created by later points with x as ptA
-                    switch (i) {
-                        case 6: qq = x + 1; kk = 1; break;
-                        case 7: qq = x + 2; kk = 5; break;
-                        case 8: qq = x + W - 1; kk = 3; break;
-                        case 9: qq = x + W; kk = 0; break;
-                        case 10: qq = x + W + 1; kk = 2; break;
-                        default: qq = x + 2 * W; kk = 4; break;
+            bool moved = false;
+            if (!(pa && pb)) {
+                const T e0 = Pa.x - Pb.x, e1 = Pa.y - Pb.y, e2 = Pa.z - Pb.z;
+                const T c11 = rst * T(1.1);
+                if (FAST) {
+                    const T qd = e0 * e0 + e1 * e1 + e2 * e2;
+                    const T ct = rst * P.tear_thresh;
+                    if (qd > ct * ct) misc[2] = 1;
+                    if (qd > c11 * c11) {
+                        const T fac = T(1) - c11 * rsqrtf((float)qd);     // (l - rest*1.1) / l
+                        const T fa = pa ? T(0) : (pb ? fac : fac * T(0.5));
+                        const T fb = pb ? T(0) : (pa ? fac : fac * T(0.5));
+                        moved = true;
+                        Pa = mk4(Pa.x - e0 * fa, Pa.y - e1 * fa, Pa.z - e2 * fa, Pa.w);
+                        Pb = mk4(Pb.x + e0 * fb, Pb.y + e1 * fb, Pb.z + e2 * fb, Pb.w);
                     }
-                }
-                const int s2 = qq * 6 + kk;
-                if (moved && qq < N && s2 > s) {
-                    const int r2 = qq / W, c2 = qq - r2 * W;
-                    const int aa = qq - koff(kk);
-                    // for i >= 6 the spring must really connect x: kvalid() rules out row wrap-around
-                    if (kvalid(r2, c2, kk) && (i < 6 || aa == x)) {
-                        if (spring_flagged(pos[aa], pos[qq], rest_of(qq, kk))) atomicOr(&ev[s2 >> 5], 1u << (s2 & 31));
+                } else {
+                    const T l = norm3(e0, e1, e2);
+                    if (l > rst * P.tear_thresh) misc[2] = 1;
+                    if (l > c11) {
+                        const T d0 = e0 / l, d1 = e1 / l, d2 = e2 / l;
+                        const T extra = l - c11;
+                        moved = true;
+                        if (pa) { Pb = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w); }
+                        else if (pb) { Pa = mk4(Pa.x - d0 * extra, Pa.y - d1 * extra, Pa.z - d2 * extra, Pa.w); }
+                        else {
+                            const T ed = extra * T(0.5);
+                            Pa = mk4(Pa.x - d0 * ed, Pa.y - d1 * ed, Pa.z - d2 * ed, Pa.w);
+                            Pb = mk4(Pb.x + d0 * ed, Pb.y + d1 * ed, Pb.z + d2 * ed, Pb.w);
+                        }
                     }
                 }
             }
+            int cand = 0x7fffffff;
+            if (moved) {   // warp-uniform
+                if (prof_on && tid == replay_warp * 32) pacc[13] += 1;
+                if (lane == 0) { if (!pa) pos[a] = Pa; if (!pb) pos[q] = Pb; }
+                // re-test my incident spring against the updated end point, in registers.  The squared terms make
+                // the test independent of which end is ptA, so no lane-divergent code is needed.
+                const bool x_moved = lane < 12 ? !pa : !pb;
+                const P4 Px = lane < 12 ? Pa : Pb;
+                if (inc_ok && x_moved && !(Px.w != T(0) && Po.w != T(0)) &&
+                    longer_than(Px.x - Po.x, Px.y - Po.y, Px.z - Po.z, limit_c(rst2))) {
+                    atomicOr(&ev[s2 >> 5], 1u << (s2 & 31));
+                    cand = s2;
+                }
+            }
+            // next pop = min(flags already in the queue, flags raised just now)
+            if (word) { const int e = ((wi0 + lane) << 5) + __ffs(word) - 1; cand = e < cand ? e : cand; }
+            int nxt = __reduce_min_sync(0xffffffffu, cand);
             __syncwarp();
+            if (nxt == 0x7fffffff && wi0 + 32 < nw) nxt = next_flagged((wi0 + 32) << 5);
+            s = nxt;
         }
         // the queue is left clean for the next substep
         for (int j = lane; j < nw; j += 32) ev[j] = 0u;
@@ -554,7 +703,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         if (prof_on && tid == 0) { const long long t = clock64(); pacc[k] += t - plast; plast = t; }
     }
     // ---- one Cloth.update() (cloth.pyx:169-214), reference order ----
-    __device__ void update_reference_order() {
+    __device__ __forceinline__ void update_reference_order() {
         if (prof_on && tid == 0) plast = clock64();
         hooke_verlet();            sync(); ptick(0);
         commit_and_hash();         sync(); ptick(1);
@@ -566,14 +715,14 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         if (prof_on && tid == 0) pacc[11] += misc[1];
         collide_replay();          sync(); ptick(7);
         limit_snapshot();          sync(); ptick(8);
-        limit_replay();
+        limit_replay(rot % NWARPS);
         if (tid == 0) { misc[0] = 0; misc[1] = 0; }
         sync(); ptick(9);
     }
 
     // ---- Gripper (gripper.pyx) ----
     // adjust (gripper.pyx:55-66): a point listed m times in grabbed_pts is moved m times
-    __device__ void gripper_adjust(T dx, T dy, T dz) {
+    __device__ __forceinline__ void gripper_adjust(T dx, T dy, T dz) {
         for (int p = tid; p < N; p += NT) {
             P4 Q = prev[p];
             if (Q.w > T(0)) {
@@ -588,7 +737,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         }
     }
     // release (gripper.pyx:68-73)
-    __device__ void gripper_release() {
+    __device__ __forceinline__ void gripper_release() {
         for (int p = tid; p < N; p += NT) {
             P4 Q = prev[p];
             if (Q.w > T(0)) {
@@ -600,7 +749,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     }
     // grab_top (gripper.pyx:23-42) in double.  Returns len(grabbed_pts) afterwards (all threads).
     // scratch: doubles in the (idle) hash table area.
-    __device__ int grab_top(double x, double y, double radius) {
+    __device__ __forceinline__ int grab_top(double x, double y, double radius) {
         double *levels = reinterpret_cast<double *>(tkey);
         const int nlev = P.n_levels;
         if (tid == 0) {
@@ -648,7 +797,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     }
 
     // bit p set <=> point p is in gripper.grabbed_pts
-    __device__ void write_grab_mask(uint32_t *out) {
+    __device__ __forceinline__ void write_grab_mask(uint32_t *out) {
         const int nwords = (N + 31) >> 5;
         for (int wi = tid; wi < nwords; wi += NT) {
             uint32_t word = 0;
@@ -674,7 +823,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     }
     // Andrew monotone chain + shoelace in double, same operation order as oracle_hull_area.
     // Uses the hash table area as scratch (the table is rebuilt from scratch every substep).
-    __device__ double hull_area() {
+    __device__ __forceinline__ double hull_area() {
         uint16_t *idx = reinterpret_cast<uint16_t *>(tkey);   // [np2]
         uint16_t *hull = reinterpret_cast<uint16_t *>(tinfo); // [2N]
         int np2 = 1; while (np2 < N) np2 <<= 1;
@@ -731,7 +880,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
 
     // block-wide double sum (result valid in all threads); scratch = first words of tinfo, which is
     // idle (all zero) outside update() and is zeroed again before returning
-    __device__ double block_sum(double v) {
+    __device__ __forceinline__ double block_sum(double v) {
         double *buf = reinterpret_cast<double *>(tinfo);
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         sync();
@@ -745,7 +894,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         return s;
     }
     // _compute_variance (cloth_env.py:1075-1084)
-    __device__ double variance_inv() {
+    __device__ __forceinline__ double variance_inv() {
         double s = 0.0;
         for (int p = tid; p < N; p += NT) s += (double)pos[p].z;
         const double mean = block_sum(s) / N;
@@ -755,7 +904,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         return (var < 0.000001) ? 1000.0 : 0.001 / var;
     }
     // _out_of_bounds (cloth_env.py:1020-1045): bounds (1,1,1), slack 0.25
-    __device__ bool out_of_bounds() {
+    __device__ __forceinline__ bool out_of_bounds() {
         int bad = 0;
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];

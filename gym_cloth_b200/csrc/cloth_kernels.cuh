@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     }
     for (int j = tid; j < P.table_size; j += NT) { c.tkey[j] = CLOTH_KEY_EMPTY; c.tinfo[j] = 0u; }
     for (int j = tid; j < P.ev_words; j += NT) c.ev[j] = 0u;
-    if (tid < 16) c.misc[tid] = 0;
+    if (tid < 16) { c.misc[tid] = 0; c.pacc[tid] = 0; }
     int flags_in = A.flags ? A.flags[env] : 0;
     mbar_wait(bar, 0);
     c.sync();
@@ -48,35 +48,39 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     if (tid == 0 && (flags_in & CLOTHB200_FLAG_BADSTATE)) c.misc[3] = 1;
     c.sync();
 
-    int nupd = 0, ngrab = -1, iters_pull = 0;
-    if (A.mode == KMODE_STEP) {
+    int nupd = 0, ngrab = -1;
+    // one loop (one inlined copy of Cloth.update) serves both the action and the bare-update mode
+    int iterations = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    T dxr = T(0), dyr = T(0);
+    const bool stepping = A.mode == KMODE_STEP;
+    if (stepping) {
         const ClothB200Plan plan = A.plans[env];
-        iters_pull = plan.iters_pull;
         ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
         if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
         // _pull thresholds (cloth_env.py:352-367, 472-475): `i < t` for integer i <=> i < ceil(t)
         const double iu = A.iters_up_env ? A.iters_up_env[env] : P.iu;
         const double t1 = iu + P.iur, t2 = t1 + (double)plan.iters_pull, t3 = t2 + P.igr, t4 = t3 + P.ir;
-        const int e0 = (int)ceil(iu), e1 = (int)ceil(t1), e2 = (int)ceil(t2), e3 = (int)ceil(t3);
-        const int iterations = ngrab == 0 ? 0 : (int)ceil(t4);   // cloth_env.py:490-493
-        const T dxr = (T)plan.dxr, dyr = (T)plan.dyr;
-        bool released = false;
-        for (int i = 0; i < iterations; i++) {
+        e0 = (int)ceil(iu); e1 = (int)ceil(t1); e2 = (int)ceil(t2); e3 = (int)ceil(t3);
+        iterations = ngrab == 0 ? 0 : (int)ceil(t4);   // cloth_env.py:490-493
+        dxr = (T)plan.dxr; dyr = (T)plan.dyr;
+    } else if (A.mode == KMODE_UPDATE) {
+        iterations = A.n_updates;
+    } else if (A.mode == KMODE_GRAB) {
+        ngrab = c.grab_top(A.grab_xy[2 * env], A.grab_xy[2 * env + 1], A.grab_radius);
+        if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+    }
+    bool released = false;
+    for (int i = 0; i < iterations; i++) {
+        if (stepping) {
             if (i < e0) { c.gripper_adjust(T(0.0), T(0.0), T(0.0025)); c.sync(); }
             else if (i < e1) { }
             else if (i < e2) { c.gripper_adjust(dxr, dyr, T(0.0)); c.sync(); }
             else if (i < e3) { }
             else if (!released) { c.gripper_release(); released = true; c.sync(); }
-            c.update_reference_order();
-            nupd++;
-            if (c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
         }
-    } else if (A.mode == KMODE_UPDATE) {
-        for (int i = 0; i < A.n_updates; i++) c.update_reference_order();
-        nupd = A.n_updates;
-    } else if (A.mode == KMODE_GRAB) {
-        ngrab = c.grab_top(A.grab_xy[2 * env], A.grab_xy[2 * env + 1], A.grab_radius);
-        if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+        c.update_reference_order();
+        nupd++;
+        if (stepping && c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
     }
 
     // ---- reward terms ----
@@ -136,7 +140,6 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         c.pacc[10] = nupd;
         for (int i = 0; i < 16; i++) A.prof[(size_t)env * 16 + i] = c.pacc[i];
     }
-    (void)iters_pull;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,6 +237,13 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     const double cw = 3 * dx, ch = 3 * dy;
     P.cell_w = (T)cw; P.cell_h = (T)ch; P.cell_t = (T)(cw > ch ? cw : ch);
     P.thresh = (T)(2.0 * hp.thickness);
+    P.thresh2 = P.thresh * P.thresh;
+    P.inv_cell_w = (T)(1.0 / cw); P.inv_cell_h = (T)(1.0 / ch); P.inv_cell_t = (T)(1.0 / (cw > ch ? cw : ch));
+    {
+        int e1, e2;
+        const bool p2w = frexp(cw, &e1) == 0.5, p2h = frexp(ch, &e2) == 0.5;
+        P.cell_pow2 = (p2w && p2h) ? 1 : 0;
+    }
     P.sim_steps = (T)hp.simulation_steps;
     P.min_z = (T)hp.minimum_z;
     P.fric1 = (T)(1. - hp.plane_friction);
