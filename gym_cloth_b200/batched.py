@@ -46,6 +46,13 @@ class BatchedCloth(object):
         self.num_steps = z(n); self.num_sim_steps = z(n)
         self.reward = z(n, dt=torch.float64); self.done = z(n)
         self.plans = torch.zeros(n, C.sizeof(_l.Plan), dtype=torch.uint8, device=dev)
+        # longest-first scheduling state: measured cycles/substep per env + scratch for the on-device sort
+        self.cost = torch.zeros(n, dtype=torch.float32, device=dev)
+        n2 = 1
+        while n2 < max(n, 1):
+            n2 *= 2
+        self.sched_scratch = torch.zeros(8 * n2 + 4 * n, dtype=torch.uint8, device=dev)
+        self.schedule = True
         self.iters_up_env = None
         self.env_order = None
         self.rest = None
@@ -84,6 +91,8 @@ class BatchedCloth(object):
             s.done = self.done.data_ptr()
         s.iters_up_env = self.iters_up_env.data_ptr() if self.iters_up_env is not None else None
         s.env_order = self.env_order.data_ptr() if self.env_order is not None else None
+        s.cost = self.cost.data_ptr()
+        s.sched_scratch = self.sched_scratch.data_ptr() if (self.schedule and self.env_order is None) else None
         return s
 
     # ------------------------------------------------------------------ construction (Cloth.__init__)

@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -14,6 +17,7 @@
 namespace clothb200 {
 std::atomic<long long> g_launch_count{0};
 long long *g_prof_ptr = nullptr;
+int g_debug_flags = [] { const char *s = getenv("CLOTHB200_DEBUG"); return s ? atoi(s) : 0; }();
 static thread_local std::string g_cuda_err;
 void set_cuda_error(cudaError_t e, const char *where) {
     g_cuda_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -25,6 +29,57 @@ int threads_per_cloth() {
         return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 128;
     }();
     return nt;
+}
+int sweep_threshold() {
+    static int v = [] { const char *s = getenv("CLOTHB200_SWEEP_THRESH"); return s ? atoi(s) : 128; }();
+    return v;
+}
+// Static dependency-level schedule of the spring list (cloth.pyx:135-146 order).  A few KB of device memory per
+// (device, grid width), built once and kept for the life of the process: the one exception to "the library owns no
+// persistent device memory".
+const uint32_t *get_sweep_table(int W, int *levels, int *lw) {
+    struct Entry { uint32_t *dev; int levels, lw; };
+    static std::map<std::pair<int, int>, Entry> cache;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { *levels = 0; *lw = 0; return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, W});
+    if (it == cache.end()) {
+        const int N = W * W;
+        if (N > 4096 || sweep_threshold() <= 0) { cache[{dev, W}] = {nullptr, 0, 0}; it = cache.find({dev, W}); }
+        else {
+            std::vector<int> last(N, 0);
+            std::vector<std::vector<uint32_t>> per_level;
+            const int offs[6] = {W, 1, W + 1, W - 1, 2 * W, 2};
+            for (int q = 0; q < N; q++) {
+                const int r = q / W, c = q % W;
+                const bool ok[6] = {r > 0, c > 0, r > 0 && c > 0, r > 0 && c + 1 < W, r > 1, c > 1};
+                for (int k = 0; k < 6; k++) if (ok[k]) {
+                    const int a = q - offs[k];
+                    const int l = 1 + (last[a] > last[q] ? last[a] : last[q]);
+                    last[a] = l; last[q] = l;
+                    if ((int)per_level.size() < l) per_level.resize(l);
+                    per_level[l - 1].push_back((uint32_t)a | ((uint32_t)q << 12) | ((uint32_t)k << 24));
+                }
+            }
+            size_t width = 0;
+            for (auto &v : per_level) width = v.size() > width ? v.size() : width;
+            int w2 = 1; while (w2 < (int)width) w2 <<= 1;
+            Entry en{nullptr, (int)per_level.size(), w2};
+            if (w2 <= 32) {
+                std::vector<uint32_t> flat((size_t)en.levels * w2, 0xffffffffu);
+                for (int l = 0; l < en.levels; l++) for (size_t i = 0; i < per_level[l].size(); i++) flat[(size_t)l * w2 + i] = per_level[l][i];
+                if (cudaMalloc((void **)&en.dev, flat.size() * 4) == cudaSuccess)
+                    cudaMemcpy(en.dev, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice);
+                else en.dev = nullptr;
+            }
+            cache[{dev, W}] = en;
+            it = cache.find({dev, W});
+        }
+    }
+    *levels = it->second.levels; *lw = it->second.lw;
+    return it->second.dev;
 }
 // typed entry points (cloth_f32.cu / cloth_f64.cu)
 #define DECL_TYPED(SFX, T)                                                                                                               \

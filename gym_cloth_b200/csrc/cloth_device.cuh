@@ -61,6 +61,10 @@ template <typename T> struct DevParams {
     T rest_k[6];                 // rest lengths of the flat grid per spring kind k (used when rest == NULL)
     double grip_radius, thickness, gripper_height;
     double iu, iur, igr, ir;     // iters_up, iters_up_rest, iters_grip_rest, iters_rest
+    // static wavefront schedule of _limit_spring_changes: springs grouped by dependency level (level(s) = 1 + max level
+    // of the earlier springs that share a point with s), sweep_lw entries per level: a | q << 12 | k << 24, ~0u = empty
+    const uint32_t *sweep_tbl;
+    int sweep_levels, sweep_lw, sweep_thresh;
 };
 
 template <typename T> struct StepArgs {
@@ -85,6 +89,8 @@ template <typename T> struct StepArgs {
     const double *iters_up_env;
     const int32_t *env_order;
     long long *prof;             // optional [n_env][16] cycle / event counters (debug)
+    float *cost;                 // optional [n_env] in/out: SM cycles per substep of the env's last step
+    int debug_flags;             // CLOTHB200_DEBUG env var: 1 = no warp-role rotation
 };
 
 enum { KMODE_STEP = 0, KMODE_UPDATE = 1, KMODE_GRAB = 2, KMODE_MEASURE = 3 };
@@ -152,6 +158,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     uint16_t *lstA, *lstB;   // [N]    bucket member lists: unordered / index-ordered; lstA later = fix-up work list
     uint32_t *ev;            // [ev_words] stretched-spring queue
     int *misc;               // [16] counters/flags: 0 total, 1 nwork, 2 tear, 3 bad, 4.. scratch
+    float2 *kc;              // [8] per spring kind: {rest*1.1, (rest*tear_thresh)^2} (f32, constant rest lengths)
     const T *rest;           // rest table of this env (REST_TABLE)
     int rot;                 // blockIdx-derived rotation of the warp roles (spreads serial phases over the 4 SM sub-partitions)
     long long *pacc;         // [16] smem: thread 0's cycles per phase + event counters when profiling
@@ -169,12 +176,13 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         ev = reinterpret_cast<uint32_t *>(smem + o); o += 4 * (size_t)((P.ev_words + 3) & ~3);
         misc = reinterpret_cast<int *>(smem + o); o += 4 * 16;
         pacc = reinterpret_cast<long long *>(smem + o); o += 8 * 16;
+        kc = reinterpret_cast<float2 *>(smem + o); o += 8 * 8;
         pslot = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
         lstA = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
         lstB = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
     }
     static __host__ __device__ size_t smem_bytes(int N, int table_size, int ev_words) {
-        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 4 * (size_t)((ev_words + 3) & ~3) + 64 + 128 +
+        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 4 * (size_t)((ev_words + 3) & ~3) + 64 + 128 + 64 +
                3 * 2 * (size_t)((N + 7) & ~7) + 16 /* mbarrier */;
     }
 
@@ -345,74 +353,37 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             lstA[idx] = (uint16_t)p;
         }
     }
-    // pass 4: rank inside the bucket -> index-ordered list (the dict value order of cloth.pyx:301-305)
-    __device__ __forceinline__ void order_members() {
+    // pass 4: rank inside the bucket -> index-ordered list (the dict value order of cloth.pyx:301-305), fused with
+    // the snapshot collision test: every pair is tested once, by its lower-index point, and only the lowest
+    // point index that has a hit is kept per bucket (a hit makes every unpinned end of the pair a "hit point").
+    __device__ __forceinline__ void order_and_snapshot() {
         for (int p = tid; p < N; p += NT) {
-            const uint32_t info = tinfo[pslot[p] & 0x7fffu];
+            const uint32_t slot = pslot[p] & 0x7fffu;
+            const uint32_t info = tinfo[slot];
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
             int rk = 0;
-            for (int j = 0; j < cnt; j++) rk += (lstA[start + j] < p) ? 1 : 0;
+            if (cnt > 1) {
+                const P4 Pp = pos[p];
+                int first = CLOTH_FIRST_NONE;
+                for (int j = 0; j < cnt; j++) {
+                    const int q = lstA[start + j];
+                    rk += (q < p) ? 1 : 0;
+                    if (q > p) {
+                        const P4 Pq = pos[q];
+                        const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+                        if (within_thresh(d0 * d0 + d1 * d1 + d2 * d2)) {
+                            const int h = Pp.w == T(0) ? p : (Pq.w == T(0) ? q : CLOTH_FIRST_NONE);
+                            first = h < first ? h : first;
+                        }
+                    }
+                }
+                if (first != CLOTH_FIRST_NONE) atomicMin(&tkey[slot], first);
+            }
             lstB[start + rk] = (uint16_t)p;
         }
     }
 
-    // ---- self_collide (cloth.pyx:313-343) of point p against its bucket, current positions ----
-    __device__ __forceinline__ int collide_point(int p, const P4 &Pp, int start, int cnt, T &cx, T &cy, T &cz) {
-        T t0 = T(0), t1 = T(0), t2 = T(0);
-        int n = 0;
-        for (int j = 0; j < cnt; j++) {
-            const int q = lstB[start + j];
-            if (q == p) continue;
-            const P4 Pq = pos[q];
-            const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-            const T qq = d0 * d0 + d1 * d1 + d2 * d2;
-            if (within_thresh(qq)) {
-                if (qq == T(0)) { misc[3] = 1; continue; }
-                T factor;
-                if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);     // (thresh-d)/d
-                else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
-                t0 += d0 * factor; t1 += d1 * factor; t2 += d2 * factor;
-                n += 1;
-            }
-        }
-        if (n) {
-            T nf = (T)n;
-            cx = t0 / nf / P.sim_steps; cy = t1 / nf / P.sim_steps; cz = t2 / nf / P.sim_steps;
-        }
-        return n;
-    }
-    // snapshot evaluation of every point: only records, per bucket, the first point that has a hit
-    __device__ __forceinline__ void collide_snapshot() {
-        for (int p = tid; p < N; p += NT) {
-            const P4 Pp = pos[p];
-            if (Pp.w != T(0)) continue;
-            const uint32_t slot = pslot[p] & 0x7fffu;
-            const uint32_t info = tinfo[slot];
-            const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
-            if (cnt < 2) continue;
-            bool hit = false;
-            int j = 0;
-            for (; j + 4 <= cnt; j += 4) {       // four candidates in flight
-                const int q0 = lstB[start + j], q1 = lstB[start + j + 1], q2 = lstB[start + j + 2], q3 = lstB[start + j + 3];
-                const P4 Q0 = pos[q0], Q1 = pos[q1], Q2 = pos[q2], Q3 = pos[q3];
-                const T a0 = Pp.x - Q0.x, a1 = Pp.y - Q0.y, a2 = Pp.z - Q0.z;
-                const T b0 = Pp.x - Q1.x, b1 = Pp.y - Q1.y, b2 = Pp.z - Q1.z;
-                const T c0 = Pp.x - Q2.x, c1 = Pp.y - Q2.y, c2 = Pp.z - Q2.z;
-                const T e0 = Pp.x - Q3.x, e1 = Pp.y - Q3.y, e2 = Pp.z - Q3.z;
-                hit |= (q0 != p) && within_thresh(a0 * a0 + a1 * a1 + a2 * a2);
-                hit |= (q1 != p) && within_thresh(b0 * b0 + b1 * b1 + b2 * b2);
-                hit |= (q2 != p) && within_thresh(c0 * c0 + c1 * c1 + c2 * c2);
-                hit |= (q3 != p) && within_thresh(e0 * e0 + e1 * e1 + e2 * e2);
-            }
-            for (; j < cnt; j++) {
-                const int q0 = lstB[start + j];
-                const P4 Q0 = pos[q0];
-                const T a0 = Pp.x - Q0.x, a1 = Pp.y - Q0.y, a2 = Pp.z - Q0.z;
-                hit |= (q0 != p) && within_thresh(a0 * a0 + a1 * a1 + a2 * a2);
-            }
-            if (hit) atomicMin(&tkey[slot], p);
-        }
-    }
+    // ---- self_collide (cloth.pyx:313-343) ----
     // _handle_plane_collision (cloth.pyx:345-370)
     __device__ __forceinline__ void plane_point(int p) {
         const P4 Pp = pos[p];
@@ -424,28 +395,22 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         T cx = gx - Q.x, cy = gy - Q.y, cz = gz - Q.z;
         pos[p] = mk4(Q.x + cx * P.fric1, Q.y + cy * P.fric1, Q.z + cz * P.fric1, Pp.w);
     }
-    // first hit points take their snapshot correction and queue their bucket for the ordered replay;
+    // buckets whose snapshot has a hit are queued for the ordered replay (by their first hit point's owner);
     // points of buckets without any hit are final and get their plane collision here.
-    __device__ __forceinline__ void collide_first_and_plane() {
+    __device__ __forceinline__ void collide_queue_and_plane() {
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];
             if (Pp.w != T(0)) continue;
             const uint32_t slot = pslot[p] & 0x7fffu;
             const int first = tkey[slot];
-            // A bucket with a hit is finished by collide_replay(): its members must keep their
-            // pre-plane positions while the first hit point re-reads them below.
-            if (first == CLOTH_FIRST_NONE) { plane_point(p); continue; }
-            if (first == p) {
-                const uint32_t info = tinfo[slot];
-                const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
-                T cx, cy, cz;
-                if (collide_point(p, Pp, start, cnt, cx, cy, cz)) pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
-                lstA[atomicAdd(&misc[1], 1)] = (uint16_t)slot;
-            }
+            // A bucket with a hit is finished by collide_replay(), plane collision included: its members must keep
+            // their pre-plane positions while the replay reads them.
+            if (first == CLOTH_FIRST_NONE) plane_point(p);
+            else if (first == p) lstA[atomicAdd(&misc[1], 1)] = (uint16_t)slot;
         }
     }
-    // ordered replay of one bucket by one warp: points after the first hit, in index order;
-    // lanes evaluate candidates, contributions are summed in candidate order.
+    // ordered replay of one bucket by one warp: from the first hit point on (nothing before it moved, so its
+    // own evaluation equals the snapshot), in index order; contributions are summed in candidate order.
     __device__ __forceinline__ void collide_replay() {
         const int nwork = misc[1];
         for (int wi = (warp + NWARPS - rot % NWARPS) % NWARPS; wi < nwork; wi += NWARPS) {
@@ -460,32 +425,29 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                 if (m) { j0 = base + __ffs(m) - 1; break; }
             }
             if (cnt <= 32) {
-                // common case: the whole bucket fits the warp; every lane keeps its member's index, positions
-                // are re-read after each update (only one member moves per step)
+                // common case: the bucket fits the warp.  Lane l keeps member l's position in registers; the point
+                // being replayed is broadcast with shuffles, so a step costs no shared-memory round trip.
                 const int mine = lane < cnt ? lstB[start + lane] : 0;
-                for (int j = j0 + 1; j < cnt; j++) {
-                    const int p = __shfl_sync(0xffffffffu, mine, j);
-                    const P4 Pp = pos[p];
-                    if (Pp.w != T(0)) continue;
-                    T c0 = T(0), c1 = T(0), c2 = T(0);
-                    bool hit = false;
-                    if (lane < cnt && lane != j) {
-                        const P4 Pq = pos[mine];
-                        const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-                        const T qq = d0 * d0 + d1 * d1 + d2 * d2;
-                        if (within_thresh(qq)) {
-                            if (qq == T(0)) misc[3] = 1;
-                            else {
-                                T factor;
-                                if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
-                                else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
-                                c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
-                                hit = true;
-                            }
-                        }
-                    }
+                P4 Pm = pos[mine];
+                bool dirty = false;
+                for (int j = j0; j < cnt; j++) {
+                    const T pw = __shfl_sync(0xffffffffu, Pm.w, j);
+                    if (pw != T(0)) continue;
+                    const T px = __shfl_sync(0xffffffffu, Pm.x, j), py = __shfl_sync(0xffffffffu, Pm.y, j),
+                            pz = __shfl_sync(0xffffffffu, Pm.z, j);
+                    const T d0 = px - Pm.x, d1 = py - Pm.y, d2 = pz - Pm.z;
+                    const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                    const bool hit = lane < cnt && lane != j && within_thresh(qq);
                     unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (m) {
+                        T c0 = T(0), c1 = T(0), c2 = T(0);
+                        if (hit) {
+                            if (qq == T(0)) misc[3] = 1;
+                            T factor;
+                            if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                            else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                            c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
+                        }
                         const int n = __popc(m);
                         T t0 = T(0), t1 = T(0), t2 = T(0);
                         while (m) {
@@ -495,18 +457,28 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                             t1 += __shfl_sync(0xffffffffu, c1, l);
                             t2 += __shfl_sync(0xffffffffu, c2, l);
                         }
-                        if (lane == 0) {
-                            const T nf = (T)n;
-                            const T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
-                            pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
-                        }
-                        __syncwarp();
+                        const T nf = (T)n;
+                        T cx, cy, cz;
+                        if (FAST) { const T inv = T(1) / (nf * P.sim_steps); cx = t0 * inv; cy = t1 * inv; cz = t2 * inv; }
+                        else { cx = t0 / nf / P.sim_steps; cy = t1 / nf / P.sim_steps; cz = t2 / nf / P.sim_steps; }
+                        if (lane == j) { Pm = mk4(px + cx, py + cy, pz + cz, Pm.w); dirty = true; }
                     }
                 }
-                __syncwarp();
-                if (lane < cnt) plane_point(mine);
+                if (lane < cnt) {
+                    // plane collision (cloth.pyx:345-370) of my member, then one write-back
+                    if (Pm.w == T(0) && !(Pm.z >= P.min_z)) {
+                        const P4 Q = prev[mine];
+                        T t = (P.min_z - Q.z) * T(1.0);
+                        T tx = Q.x + t * T(-0.0), ty = Q.y + t * T(-0.0), tz = Q.z + t * T(-1.0);
+                        T gx = tx + P.surf_off * T(0.0), gy = ty + P.surf_off * T(0.0), gz = tz + P.surf_off * T(1.0);
+                        T ex = gx - Q.x, ey = gy - Q.y, ez = gz - Q.z;
+                        Pm = mk4(Q.x + ex * P.fric1, Q.y + ey * P.fric1, Q.z + ez * P.fric1, Pm.w);
+                        dirty = true;
+                    }
+                    if (dirty) pos[mine] = Pm;
+                }
             } else {
-                for (int j = j0 + 1; j < cnt; j++) {
+                for (int j = j0; j < cnt; j++) {
                     const int p = lstB[start + j];
                     const P4 Pp = pos[p];
                     if (Pp.w != T(0)) continue;
@@ -616,10 +588,14 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         const int inc_dq = i < 6 ? 0 : (i == 6 ? 1 : (i == 7 ? 2 : (i == 8 ? W - 1 : (i == 9 ? W : (i == 10 ? W + 1 : 2 * W)))));
         const int inc_k = i < 6 ? i : (i == 6 ? 1 : (i == 7 ? 5 : (i == 8 ? 3 : (i == 9 ? 0 : (i == 10 ? 2 : 4)))));
         const int inc_other = i < 6 ? -koff(inc_k) : inc_dq;   // the end point that is not x, relative to x
-        const bool lane_active = lane < 24;
-        const T rst_lane = REST_TABLE ? T(0) : sel6(P.rest_k, inc_k);
+        // spring kind inc_k exists at creating point qq=(r,c) <=> qq >= minq && cmin <= c <= cmax   (cloth.pyx:135-146)
+        const int minq = lane >= 24 ? 0x40000000 : ((inc_k == 0 || inc_k == 2 || inc_k == 3) ? W : (inc_k == 4 ? 2 * W : 0));
+        const int cmin = (inc_k == 1 || inc_k == 2) ? 1 : (inc_k == 5 ? 2 : 0);
+        const int cmax = inc_k == 3 ? W - 2 : W - 1;
+        const T c_lane = REST_TABLE ? T(0) : limit_c(sel6(P.rest_k, inc_k));
         const unsigned long long kp = koff_pack();
         const int nw = P.ev_words;
+        int npop = 0, nmove = 0;
         int s = next_flagged(0);
         while (s != 0x7fffffff) {
             const int q = (int)(((unsigned)s * 43691u) >> 18);   // s / 6 for s < 2^17
@@ -634,59 +610,58 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
             const int x = lane < 12 ? a : q;
             const int qq = x + inc_dq;
             const int s2 = qq * 6 + inc_k;
-            const int r2 = qq / W, c2 = qq - r2 * W;
-            const bool inc_ok = lane_active && qq < N && s2 > s && ((vmask(r2, c2) >> inc_k) & 1u);
+            const int c2 = qq - (qq / W) * W;
+            const bool inc_ok = qq >= minq && qq < N && s2 > s && c2 >= cmin && c2 <= cmax;
             const P4 Po = pos[inc_ok ? x + inc_other : x];
-            const T rst2 = REST_TABLE ? __ldg(rest + (inc_ok ? s2 : s)) : rst_lane;
-            const T rst = REST_TABLE ? __ldg(rest + s) : sel6(P.rest_k, k);
-            if (prof_on && tid == replay_warp * 32) pacc[12] += 1;
+            npop++;
             const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
             bool moved = false;
-            if (!(pa && pb)) {
+            if (FAST) {
+                // branch-free: the correction factor is always computed, the stores and the re-test are predicated
+                float c11, ct2;
+                if (REST_TABLE) { const float r = (float)__ldg(rest + s), ct = r * (float)P.tear_thresh; c11 = r * 1.1f; ct2 = ct * ct; }
+                else { const float2 c = kc[k]; c11 = c.x; ct2 = c.y; }
+                const float e0 = (float)(Pa.x - Pb.x), e1 = (float)(Pa.y - Pb.y), e2 = (float)(Pa.z - Pb.z);
+                const float qd = e0 * e0 + e1 * e1 + e2 * e2;
+                const bool live = !(pa && pb);
+                moved = live && qd > c11 * c11;
+                if (live && qd > ct2) misc[2] = 1;
+                const float fac = 1.0f - c11 * rsqrtf(fmaxf(qd, 1e-30f));
+                const float fa = (!moved || pa) ? 0.0f : (pb ? fac : fac * 0.5f);
+                const float fb = (!moved || pb) ? 0.0f : (pa ? fac : fac * 0.5f);
+                Pa = mk4((T)((float)Pa.x - e0 * fa), (T)((float)Pa.y - e1 * fa), (T)((float)Pa.z - e2 * fa), Pa.w);
+                Pb = mk4((T)((float)Pb.x + e0 * fb), (T)((float)Pb.y + e1 * fb), (T)((float)Pb.z + e2 * fb), Pb.w);
+            } else if (!(pa && pb)) {
+                const T rst = REST_TABLE ? __ldg(rest + s) : sel6(P.rest_k, k);
                 const T e0 = Pa.x - Pb.x, e1 = Pa.y - Pb.y, e2 = Pa.z - Pb.z;
                 const T c11 = rst * T(1.1);
-                if (FAST) {
-                    const T qd = e0 * e0 + e1 * e1 + e2 * e2;
-                    const T ct = rst * P.tear_thresh;
-                    if (qd > ct * ct) misc[2] = 1;
-                    if (qd > c11 * c11) {
-                        const T fac = T(1) - c11 * rsqrtf((float)qd);     // (l - rest*1.1) / l
-                        const T fa = pa ? T(0) : (pb ? fac : fac * T(0.5));
-                        const T fb = pb ? T(0) : (pa ? fac : fac * T(0.5));
-                        moved = true;
-                        Pa = mk4(Pa.x - e0 * fa, Pa.y - e1 * fa, Pa.z - e2 * fa, Pa.w);
-                        Pb = mk4(Pb.x + e0 * fb, Pb.y + e1 * fb, Pb.z + e2 * fb, Pb.w);
-                    }
-                } else {
-                    const T l = norm3(e0, e1, e2);
-                    if (l > rst * P.tear_thresh) misc[2] = 1;
-                    if (l > c11) {
-                        const T d0 = e0 / l, d1 = e1 / l, d2 = e2 / l;
-                        const T extra = l - c11;
-                        moved = true;
-                        if (pa) { Pb = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w); }
-                        else if (pb) { Pa = mk4(Pa.x - d0 * extra, Pa.y - d1 * extra, Pa.z - d2 * extra, Pa.w); }
-                        else {
-                            const T ed = extra * T(0.5);
-                            Pa = mk4(Pa.x - d0 * ed, Pa.y - d1 * ed, Pa.z - d2 * ed, Pa.w);
-                            Pb = mk4(Pb.x + d0 * ed, Pb.y + d1 * ed, Pb.z + d2 * ed, Pb.w);
-                        }
+                const T l = norm3(e0, e1, e2);
+                if (l > rst * P.tear_thresh) misc[2] = 1;
+                if (l > c11) {
+                    const T d0 = e0 / l, d1 = e1 / l, d2 = e2 / l;
+                    const T extra = l - c11;
+                    moved = true;
+                    if (pa) { Pb = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w); }
+                    else if (pb) { Pa = mk4(Pa.x - d0 * extra, Pa.y - d1 * extra, Pa.z - d2 * extra, Pa.w); }
+                    else {
+                        const T ed = extra * T(0.5);
+                        Pa = mk4(Pa.x - d0 * ed, Pa.y - d1 * ed, Pa.z - d2 * ed, Pa.w);
+                        Pb = mk4(Pb.x + d0 * ed, Pb.y + d1 * ed, Pb.z + d2 * ed, Pb.w);
                     }
                 }
             }
             int cand = 0x7fffffff;
-            if (moved) {   // warp-uniform
-                if (prof_on && tid == replay_warp * 32) pacc[13] += 1;
-                if (lane == 0) { if (!pa) pos[a] = Pa; if (!pb) pos[q] = Pb; }
+            nmove += moved ? 1 : 0;
+            if (lane == 0 && moved) { if (!pa) pos[a] = Pa; if (!pb) pos[q] = Pb; }
+            {
                 // re-test my incident spring against the updated end point, in registers.  The squared terms make
                 // the test independent of which end is ptA, so no lane-divergent code is needed.
                 const bool x_moved = lane < 12 ? !pa : !pb;
                 const P4 Px = lane < 12 ? Pa : Pb;
-                if (inc_ok && x_moved && !(Px.w != T(0) && Po.w != T(0)) &&
-                    longer_than(Px.x - Po.x, Px.y - Po.y, Px.z - Po.z, limit_c(rst2))) {
-                    atomicOr(&ev[s2 >> 5], 1u << (s2 & 31));
-                    cand = s2;
-                }
+                const T cl = REST_TABLE ? limit_c(__ldg(rest + (inc_ok ? s2 : s))) : c_lane;
+                const bool flag = moved && inc_ok && x_moved && !(Px.w != T(0) && Po.w != T(0)) &&
+                                  longer_than(Px.x - Po.x, Px.y - Po.y, Px.z - Po.z, cl);
+                if (flag) { atomicOr(&ev[s2 >> 5], 1u << (s2 & 31)); cand = s2; }
             }
             // next pop = min(flags already in the queue, flags raised just now)
             if (word) { const int e = ((wi0 + lane) << 5) + __ffs(word) - 1; cand = e < cand ? e : cand; }
@@ -697,6 +672,112 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         }
         // the queue is left clean for the next substep
         for (int j = lane; j < nw; j += 32) ev[j] = 0u;
+        if (prof_on && lane == 0) { pacc[12] += npop; pacc[13] += nmove; }
+    }
+
+    // Wavefront sweep of the whole limit pass by one warp: level order is a topological order of the sequential
+    // loop (two springs that share a point are never in the same level), so evaluating every spring level by level
+    // with lanes = springs of the level gives exactly the sequential result at a cost independent of how many
+    // springs are stretched.  Used when the queue is long.
+    // one dependency level of the sweep.  f32: branch-free (idle lanes run a dummy spring 0-0, the correction factor is
+    // computed unconditionally and stores are predicated), because divergence is what a lone warp pays most for.
+    __device__ __forceinline__ int sweep_level(uint32_t cur, T rst_tab) {
+        if (FAST) {
+            const bool on = cur != 0xffffffffu;
+            const int a = on ? (int)(cur & 0xfffu) : 0, q = on ? (int)((cur >> 12) & 0xfffu) : 0, k = (cur >> 24) & 7u;
+            const P4 Pa = pos[a], Pb = pos[q];
+            float c11, ct2;
+            if (REST_TABLE) { c11 = (float)rst_tab * 1.1f; const float ct = (float)rst_tab * (float)P.tear_thresh; ct2 = ct * ct; }
+            else { const float2 c = kc[k]; c11 = c.x; ct2 = c.y; }
+            const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
+            const float e0 = (float)(Pa.x - Pb.x), e1 = (float)(Pa.y - Pb.y), e2 = (float)(Pa.z - Pb.z);
+            const float qd = e0 * e0 + e1 * e1 + e2 * e2;
+            const bool live = on && !(pa && pb);
+            const bool str = live && qd > c11 * c11;
+            if (live && qd > ct2) misc[2] = 1;
+            const float fac = 1.0f - c11 * rsqrtf(fmaxf(qd, 1e-30f));
+            const float fa = pa ? 0.0f : (pb ? fac : fac * 0.5f);
+            const float fb = pb ? 0.0f : (pa ? fac : fac * 0.5f);
+            if (str && !pa) pos[a] = mk4((T)((float)Pa.x - e0 * fa), (T)((float)Pa.y - e1 * fa), (T)((float)Pa.z - e2 * fa), Pa.w);
+            if (str && !pb) pos[q] = mk4((T)((float)Pb.x + e0 * fb), (T)((float)Pb.y + e1 * fb), (T)((float)Pb.z + e2 * fb), Pb.w);
+            __syncwarp();
+            return str ? 1 : 0;
+        }
+        int moved = 0;
+        if (cur != 0xffffffffu) {
+            const int a = cur & 0xfffu, q = (cur >> 12) & 0xfffu, k = (cur >> 24) & 7u;
+            P4 Pa = pos[a], Pb = pos[q];
+            const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
+            if (!(pa && pb)) {
+                const T rst = REST_TABLE ? rst_tab : rest_of(q, k);
+                const T e0 = Pa.x - Pb.x, e1 = Pa.y - Pb.y, e2 = Pa.z - Pb.z;
+                const T c11 = rst * T(1.1);
+                const T l = norm3(e0, e1, e2);
+                if (l > rst * P.tear_thresh) misc[2] = 1;
+                if (l > c11) {
+                    const T d0 = e0 / l, d1 = e1 / l, d2 = e2 / l;
+                    const T extra = l - c11;
+                    if (pa) { pos[q] = mk4(Pb.x + d0 * extra, Pb.y + d1 * extra, Pb.z + d2 * extra, Pb.w); }
+                    else if (pb) { pos[a] = mk4(Pa.x - d0 * extra, Pa.y - d1 * extra, Pa.z - d2 * extra, Pa.w); }
+                    else {
+                        const T ed = extra * T(0.5);
+                        pos[a] = mk4(Pa.x - d0 * ed, Pa.y - d1 * ed, Pa.z - d2 * ed, Pa.w);
+                        pos[q] = mk4(Pb.x + d0 * ed, Pb.y + d1 * ed, Pb.z + d2 * ed, Pb.w);
+                    }
+                    moved = 1;
+                }
+            }
+        }
+        __syncwarp();
+        return moved;
+    }
+    __device__ __forceinline__ T sweep_rest(uint32_t e) const {
+        if (!REST_TABLE || e == 0xffffffffu) return T(0);
+        return __ldg(rest + ((e >> 12) & 0xfffu) * 6 + ((e >> 24) & 7u));
+    }
+    __device__ __forceinline__ void limit_sweep() {
+        const int lw = P.sweep_lw, nl = P.sweep_levels;
+        const bool lane_on = lane < lw;
+        const uint32_t *tp = P.sweep_tbl + lane;
+        // schedule entries (and, with a rest table, the rest lengths) are fetched eight levels ahead: the table lives in
+        // L2, shared memory leaves little L1
+        uint32_t cur[8], nxt[8];
+        T rcur[8], rnxt[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { cur[u] = (lane_on && u < nl) ? __ldg(tp + (size_t)u * lw) : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) rcur[u] = sweep_rest(cur[u]);
+        int nmove = 0;
+        for (int L = 0; L < nl; L += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) nxt[u] = (lane_on && L + 8 + u < nl) ? __ldg(tp + (size_t)(L + 8 + u) * lw) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                nmove += sweep_level(cur[u], rcur[u]);
+                if (u == 3) {
+#pragma unroll
+                    for (int v = 0; v < 8; v++) rnxt[v] = sweep_rest(nxt[v]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { cur[u] = nxt[u]; rcur[u] = rnxt[u]; }
+        }
+        for (int j = lane; j < P.ev_words; j += 32) ev[j] = 0u;
+        if (prof_on) {
+            for (int o = 16; o > 0; o >>= 1) nmove += __shfl_xor_sync(0xffffffffu, nmove, o);
+            if (lane == 0) { pacc[13] += nmove; pacc[5] += 1; }
+        }
+    }
+    // the replay warp picks the cheaper exact strategy for this substep
+    __device__ __forceinline__ void limit_resolve(int replay_warp) {
+        if (warp != replay_warp) return;
+        if (P.sweep_tbl != nullptr) {
+            int cnt = 0;
+            for (int j = lane; j < P.ev_words; j += 32) cnt += __popc(ev[j]);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt >= P.sweep_thresh) { limit_sweep(); return; }
+        }
+        limit_replay(replay_warp);
     }
 
     __device__ __forceinline__ void ptick(int k) {
@@ -709,13 +790,12 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         commit_and_hash();         sync(); ptick(1);
         alloc_buckets();           sync(); ptick(2);
         scatter_members();         sync(); ptick(3);
-        order_members();           sync(); ptick(4);
-        collide_snapshot();        sync(); ptick(5);
-        collide_first_and_plane(); sync(); ptick(6);
+        order_and_snapshot();      sync(); ptick(4);
+        collide_queue_and_plane(); sync(); ptick(6);
         if (prof_on && tid == 0) pacc[11] += misc[1];
         collide_replay();          sync(); ptick(7);
         limit_snapshot();          sync(); ptick(8);
-        limit_replay(rot % NWARPS);
+        limit_resolve(rot % NWARPS);
         if (tid == 0) { misc[0] = 0; misc[1] = 0; }
         sync(); ptick(9);
     }

@@ -9,6 +9,7 @@
 namespace clothb200 {
 
 extern std::atomic<long long> g_launch_count;   // defined in cloth_abi.cu
+extern int g_debug_flags;
 extern long long *g_prof_ptr;                    // debug: per-env phase counters (clothb200_debug_set_profile)
 void set_cuda_error(cudaError_t e, const char *where);
 
@@ -25,6 +26,9 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     const T *rest_env = REST_TABLE ? A.rest + (long long)env * A.rest_env_stride : nullptr;
     CTA c(P, smem, rest_env);
     c.prof_on = A.prof != nullptr;
+    unsigned long long gt0 = 0;
+    if (A.prof && threadIdx.x == 0) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0)); }
+    if (A.debug_flags & 1) c.rot = 0;
     const int N = c.N;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + CTA::smem_bytes(N, P.table_size, P.ev_words) - 16);
     const uint32_t bytes = (uint32_t)(sizeof(P4) * (size_t)N);
@@ -41,6 +45,10 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     for (int j = tid; j < P.table_size; j += NT) { c.tkey[j] = CLOTH_KEY_EMPTY; c.tinfo[j] = 0u; }
     for (int j = tid; j < P.ev_words; j += NT) c.ev[j] = 0u;
     if (tid < 16) { c.misc[tid] = 0; c.pacc[tid] = 0; }
+    if (tid < 8) {
+        const float r = (float)P.rest_k[tid < 6 ? tid : 0], ct = r * (float)P.tear_thresh;
+        c.kc[tid] = make_float2(r * 1.1f, ct * ct);
+    }
     int flags_in = A.flags ? A.flags[env] : 0;
     mbar_wait(bar, 0);
     c.sync();
@@ -70,6 +78,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
     }
     bool released = false;
+    const long long t_loop0 = clock64();
     for (int i = 0; i < iterations; i++) {
         if (stepping) {
             if (i < e0) { c.gripper_adjust(T(0.0), T(0.0), T(0.0025)); c.sync(); }
@@ -82,6 +91,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         nupd++;
         if (stepping && c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
     }
+    const long long t_loop1 = clock64();
 
     // ---- reward terms ----
     const bool want_measure = (A.coverage || A.variance_inv || A.reward) && A.mode != KMODE_GRAB;
@@ -109,6 +119,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         T *o = A.obs + (size_t)env * 3 * N;
         for (int i = tid; i < 3 * N; i += NT) { const int p = i / 3; o[i] = flat[p * 4 + (i - p * 3)]; }
     }
+    if (tid == 0 && A.cost && stepping && nupd > 0) A.cost[env] = (float)(t_loop1 - t_loop0) / (float)nupd;
     if (tid == 0) {
         int f = (tear ? CLOTHB200_FLAG_TEAR : 0) | (oob ? CLOTHB200_FLAG_OOB : 0) | (bad ? CLOTHB200_FLAG_BADSTATE : 0);
         if (A.mode == KMODE_STEP && ngrab == 0) f |= CLOTHB200_FLAG_NOGRAB;
@@ -137,9 +148,66 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         }
     }
     if (A.prof && tid == 0) {
+        unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        c.pacc[14] = (long long)gt0; c.pacc[15] = (long long)gt1; c.pacc[11] = (long long)smid * 1000000 + c.pacc[11] % 1000000;
         c.pacc[10] = nupd;
         for (int i = 0; i < 16; i++) A.prof[(size_t)env * 16 + i] = c.pacc[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// longest-first scheduling: work estimate per environment, then a single-CTA bitonic sort of (work, env)
+// ------------------------------------------------------------------------------------------------
+// One warp per environment.  work = number of substeps the plan will run (0 if the grip catches nothing)
+// x the environment's last measured cycles per substep.  This only orders the launch: it is a heuristic
+// (the z-band test is simplified), results never depend on it.
+template <typename T>
+__global__ void plan_work_kernel(int n_env, int n_pow2, int N, const T *__restrict__ pos, const T *__restrict__ prev,
+                                 const ClothB200Plan *__restrict__ plans, const float *__restrict__ cost, double grip_radius,
+                                 double thickness, double height, double iu, double iur, double igr, double ir,
+                                 const double *__restrict__ iters_up_env, unsigned long long *__restrict__ keys) {
+    const int env = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (env >= n_pow2) return;
+    if (env >= n_env) { if (lane == 0) keys[env] = ~0ull; return; }   // padding sorts last
+    const ClothB200Plan pl = plans[env];
+    const T *pp = pos + (size_t)env * N * 4, *qq = prev + (size_t)env * N * 4;
+    bool any = false;
+    for (int p = lane; p < N; p += 32) {
+        const double x = (double)pp[4 * p], y = (double)pp[4 * p + 1], z = (double)pp[4 * p + 2];
+        const bool in_r = (x - pl.gx) * (x - pl.gx) + (y - pl.gy) * (y - pl.gy) < grip_radius;
+        any |= (in_r && z > -2 * thickness && z < height + 2 * thickness) || (qq[4 * p + 3] > T(0));
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) {
+        const double i0 = iters_up_env ? iters_up_env[env] : iu;
+        const float iters = any ? (float)(i0 + iur + (double)pl.iters_pull + igr + ir) : 0.f;
+        float c = cost ? cost[env] : 0.f;
+        if (!(c > 0.f)) c = 1.0e5f;
+        const float work = iters * c;
+        // descending by work: invert the (non-negative) float bits; ties by env id
+        keys[env] = ((unsigned long long)(~__float_as_uint(work)) << 32) | (unsigned)env;
+    }
+}
+
+// bitonic sort of n_pow2 64-bit keys by one CTA (n_pow2 <= 65536), then env_order[i] = low word
+static __global__ void __launch_bounds__(1024) sort_keys_kernel(int n_env, int n_pow2, unsigned long long *__restrict__ keys,
+                                                         int32_t *__restrict__ env_order) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    const bool up = (i & k) == 0;
+                    if (up ? (a > b) : (a < b)) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n_env; i += blockDim.x) env_order[i] = (int32_t)(keys[i] & 0xffffffffull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -216,6 +284,9 @@ template <typename T> __global__ void gripper_release_kernel(size_t total_pts, T
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+const uint32_t *get_sweep_table(int W, int *levels, int *lw);   // cloth_abi.cu (cached per device and grid width)
+int sweep_threshold();
+
 template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T> &P) {
     const int W = hp.num_width_points, H = hp.num_height_points;
     P.W = W; P.H = H; P.N = W * H;
@@ -257,6 +328,8 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     for (double z = hp.gripper_height; z > 0; z -= hp.thickness) { nlev++; if (nlev > 4 * ts / 8) break; }
     P.n_levels = nlev;
     P.iu = hp.iters_up; P.iur = hp.iters_up_rest; P.igr = hp.iters_grip_rest; P.ir = hp.iters_rest;
+    P.sweep_tbl = get_sweep_table(W, &P.sweep_levels, &P.sweep_lw);
+    P.sweep_thresh = sweep_threshold();
     return 0;
 }
 

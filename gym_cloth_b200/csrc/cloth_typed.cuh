@@ -19,8 +19,10 @@ template <typename T> StepArgs<T> make_args(int n_env, const ClothB200Step *io) 
             A.reward = io->reward; A.done = io->done;
         }
         A.iters_up_env = io->iters_up_env; A.env_order = io->env_order;
+        A.cost = io->cost;
     }
     A.prof = g_prof_ptr;
+    A.debug_flags = g_debug_flags;
     return A;
 }
 
@@ -41,6 +43,22 @@ int step_plans_t(const ClothB200Params *hp, int mode, int n_env, const ClothB200
     if (mode != CLOTHB200_MODE_REFERENCE_ORDER) return CLOTHB200_ERR_UNSUPPORTED;
     StepArgs<T> A = make_args<T>(n_env, io);
     A.plans = plans; A.mode = KMODE_STEP; A.initialize = initialize;
+    if (!io->env_order && io->sched_scratch && n_env > 1 && n_env <= 65536) {
+        // longest-first schedule (heuristic ordering only; results do not depend on it)
+        int n_pow2 = 1; while (n_pow2 < n_env) n_pow2 <<= 1;
+        unsigned long long *keys = (unsigned long long *)io->sched_scratch;
+        int32_t *order = (int32_t *)(keys + n_pow2);
+        const int N = hp->num_width_points * hp->num_height_points;
+        const int warps_per_block = 8;
+        plan_work_kernel<T><<<(n_pow2 + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+            n_env, n_pow2, N, (const T *)io->pos, (const T *)io->prev, plans, io->cost, hp->grip_radius, hp->thickness,
+            hp->gripper_height, hp->iters_up, hp->iters_up_rest, hp->iters_grip_rest, hp->iters_rest, io->iters_up_env, keys);
+        sort_keys_kernel<<<1, 1024, 0, st>>>(n_env, n_pow2, keys, order);
+        g_launch_count += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_cuda_error(e, "schedule kernels"); return CLOTHB200_ERR_CUDA; }
+        A.env_order = order;
+    }
     return launch_step<T>(*hp, A, st);
 }
 

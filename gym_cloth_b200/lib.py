@@ -53,6 +53,7 @@ class Step(C.Structure):
         ("prev_coverage", C.c_void_p), ("num_steps", C.c_void_p), ("num_sim_steps", C.c_void_p),
         ("reward", C.c_void_p), ("done", C.c_void_p),
         ("iters_up_env", C.c_void_p), ("env_order", C.c_void_p),
+        ("cost", C.c_void_p), ("sched_scratch", C.c_void_p),
     ]
 
 

@@ -105,7 +105,13 @@ typedef struct ClothB200Step {
     double *reward;            /* [n_env] out */
     int32_t *done;             /* [n_env] out */
     const double *iters_up_env;/* [n_env] optional per-env override of iters_up (tier-3 reset, cloth_env.py:960) */
-    const int32_t *env_order;  /* [n_env] optional: order in which CTAs pick environments (longest first) */
+    const int32_t *env_order;  /* [n_env] optional: explicit order in which CTAs pick environments; also selects a subset
+                                  (n_env entries of a larger batch).  Overrides the built-in scheduling. */
+    float *cost;               /* [n_env] optional in/out: measured SM cycles per substep of each environment's last step
+                                  (0 = unknown); feeds the longest-first schedule */
+    void *sched_scratch;       /* optional DEVICE scratch, >= 8*pow2ceil(n_env) + 4*n_env bytes.  When given (and env_order
+                                  is NULL) step_plans/step_actions/step_host schedule environments longest-first:
+                                  work = substeps of the plan (0 if the grip catches nothing) x cost */
 } ClothB200Step;
 
 /* ---- library / device ---- */

@@ -60,6 +60,7 @@ typedef struct {
     int map_cap;
     /* instrumentation (not part of the reference): counters for design studies */
     int64_t n_updates, n_pair_tests, n_collide_hits, n_stretched, n_plane;
+    int32_t *rec; int rec_cap, rec_n;   /* optional: indices of the springs shortened by the last limit pass */
 } OracleCloth;
 
 /* cloth.pyx:17-18  fastnorm */
@@ -87,6 +88,7 @@ void oracle_cloth_destroy(OracleCloth *c) {
     free(c->pos); free(c->prev); free(c->force); free(c->pinned);
     free(c->sa); free(c->sb); free(c->stype); free(c->rest); free(c->grabbed);
     free(c->map_next); free(c->map_head); free(c->map_tail); free(c->map_key);
+    free(c->rec);
     free(c);
 }
 
@@ -186,6 +188,12 @@ void oracle_cloth_get_springs(const OracleCloth *c, int32_t *a, int32_t *b, uint
     if (rest) memcpy(rest, c->rest, c->S * sizeof(double));
 }
 void oracle_cloth_set_rest(OracleCloth *c, const double *rest) { memcpy(c->rest, rest, c->S * sizeof(double)); }
+void oracle_cloth_record_limit(OracleCloth *c, int on) {
+    if (on && !c->rec) { c->rec_cap = c->S; c->rec = (int32_t *)malloc(c->S * sizeof(int32_t)); }
+    if (!on) { free(c->rec); c->rec = NULL; }
+    c->rec_n = 0;
+}
+int oracle_cloth_get_limit_record(const OracleCloth *c, int32_t *out) { if (c->rec) memcpy(out, c->rec, c->rec_n * sizeof(int32_t)); return c->rec_n; }
 void oracle_cloth_get_counters(const OracleCloth *c, int64_t *out5) {
     out5[0] = c->n_updates; out5[1] = c->n_pair_tests; out5[2] = c->n_collide_hits;
     out5[3] = c->n_stretched; out5[4] = c->n_plane;
@@ -337,6 +345,7 @@ void oracle_phase_plane(OracleCloth *c) {
 /* cloth.pyx:258-296 */
 void oracle_phase_limit(OracleCloth *c) {
     double tear_thresh = c->P.tear_thresh;
+    c->rec_n = 0;
     for (int s = 0; s < c->S; s++) {
         int a = c->sa[s], b = c->sb[s];
         if (c->pinned[a] && c->pinned[b]) continue;
@@ -348,6 +357,7 @@ void oracle_phase_limit(OracleCloth *c) {
             double d0 = (pa[0] - pb[0]) / l, d1 = (pa[1] - pb[1]) / l, d2 = (pa[2] - pb[2]) / l;
             double extra = l - rest * 1.1;
             c->n_stretched++;
+            if (c->rec && c->rec_n < c->rec_cap) c->rec[c->rec_n++] = s;
             if (c->pinned[a]) {
                 pb[0] = pb[0] + d0 * extra; pb[1] = pb[1] + d1 * extra; pb[2] = pb[2] + d2 * extra;
             } else if (c->pinned[b]) {

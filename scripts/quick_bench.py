@@ -12,6 +12,7 @@ def actions(rng, n):
 def timed_action(n, dtype, seed=0, reps=2):
     rng = np.random.RandomState(seed)
     bc = BatchedCloth(L.default_params(), n, dtype=dtype)
+    bc.schedule = os.environ.get("NOSCHED") is None
     a0 = torch.from_numpy(actions(rng, n)).to("cuda", dtype)
     bc.step_actions(a0); torch.cuda.synchronize()          # crumple (untimed)
     res = []
@@ -20,6 +21,9 @@ def timed_action(n, dtype, seed=0, reps=2):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); bc.step_actions(a); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1); sub = int(bc.sim_steps.sum().item())
+        per_env_ms = (bc.cost.double() * bc.sim_steps.double() / 1.965e6).cpu().numpy()
+        print("   per-env busy time: max %.1f ms, p99 %.1f, mean(active) %.1f; sum/slots(888) %.1f ms; kernel %.1f ms" % (
+            per_env_ms.max(), np.percentile(per_env_ms, 99), per_env_ms[per_env_ms > 0].mean(), per_env_ms.sum() / 888, ms))
         res.append((ms, sub, sub / ms * 1e3, n / ms * 1e3, int(((bc.flags & 4) != 0).sum().item())))
     return res, bc
 
@@ -28,7 +32,7 @@ if __name__ == "__main__":
     what = sys.argv[2] if len(sys.argv) > 2 else "time"
     print("NT", os.environ.get("CLOTHB200_NT", "128"), "n", n)
     if what == "time":
-        for dt in (torch.float32, torch.float64):
+        for dt in ((torch.float32,) if os.environ.get("F32ONLY") else (torch.float32, torch.float64)):
             res, bc = timed_action(n, dt)
             for ms, sub, sps, eps, ng in res:
                 print("%s: %.1f ms, %d substeps, %.3e substeps/s, %.1f env-steps/s, nograb %d" % (str(dt), ms, sub, sps, eps, ng))
@@ -64,7 +68,7 @@ if __name__ == "__main__":
         L.lib().clothb200_debug_set_profile(None)
         p = prof.cpu().numpy().astype(np.float64)
         act = p[:, 10] > 0
-        names = ["hooke_verlet", "commit_hash", "alloc", "scatter", "order", "coll_snap", "coll_first_plane", "coll_replay", "limit_snap", "limit_replay"]
+        names = ["hooke_verlet", "commit_hash", "alloc", "scatter", "order+snap", "(unused)", "coll_first_plane", "coll_replay", "limit_snap", "limit_replay"]
         tot = p[act, :10].sum()
         nsub = p[act, 10].sum()
         print("%s: %.1f ms; active envs %d; substeps %d; cycles/substep/CTA %.0f" % (str(dt), e0.elapsed_time(e1), act.sum(), nsub, tot / nsub))
@@ -74,3 +78,46 @@ if __name__ == "__main__":
         per = p[act, :10].sum(1) / p[act, 10]
         print("  per-env cycles/substep percentiles 10/50/90/100:", np.percentile(per, [10, 50, 90, 100]).round(0))
         print("  per-env pops/substep percentiles 50/90/100:", np.percentile(p[act, 12] / p[act, 10], [50, 90, 100]).round(1))
+        heavy = act & (np.where(act, p[:, :10].sum(1) / np.maximum(p[:, 10], 1), 0) >= np.percentile(per, 95))
+        toth = p[heavy, :10].sum(); nsh = p[heavy, 10].sum()
+        print("  heaviest 5%% of envs (%d): cycles/substep %.0f, pops/substep %.1f, replay buckets/substep %.1f" % (
+            heavy.sum(), toth / nsh, p[heavy, 12].sum() / nsh, p[heavy, 11].sum() / nsh))
+        for i, nm in enumerate(names):
+            print("    %-18s %6.1f %%  %9.0f cyc/substep" % (nm, 100 * p[heavy, i].sum() / toth, p[heavy, i].sum() / nsh))
+        idx = np.argsort(-np.where(act, p[:, :10].sum(1) / np.maximum(p[:, 10], 1), 0))
+        print("  env  substeps  cyc/substep  pops/sub  moved/sub  limit_replay cyc/pop  buckets/sub  coll_replay cyc/bucket")
+        for e in list(idx[:8]) + list(idx[200:204]) + list(idx[600:604]):
+            ns = p[e, 10]
+            print("  %4d %8d %11.0f %9.1f %9.1f %12.0f %12.1f %12.0f" % (e, ns, p[e, :10].sum() / ns, p[e, 12] / ns, p[e, 13] / ns,
+                  p[e, 9] / max(p[e, 12], 1), p[e, 11] / ns, p[e, 7] / max(p[e, 11], 1)))
+    elif what == "timeline":
+        import ctypes as C
+        dt = torch.float32
+        rng = np.random.RandomState(0)
+        bc = BatchedCloth(L.default_params(), n, dtype=dt)
+        bc.schedule = os.environ.get("NOSCHED") is None
+        a0 = torch.from_numpy(actions(rng, n)).to("cuda", dt)
+        bc.step_actions(a0); torch.cuda.synchronize()
+        prof = torch.zeros(n, 16, dtype=torch.int64, device="cuda")
+        L.lib().clothb200_debug_set_profile(C.c_void_p(prof.data_ptr()))
+        a = torch.from_numpy(actions(rng, n)).to("cuda", dt)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); bc.step_actions(a); e1.record(); torch.cuda.synchronize()
+        L.lib().clothb200_debug_set_profile(None)
+        p = prof.cpu().numpy()
+        t0 = p[:, 14].min(); st = (p[:, 14] - t0) / 1e6; en = (p[:, 15] - t0) / 1e6
+        print("kernel %.1f ms; span %.1f ms" % (e0.elapsed_time(e1), en.max()))
+        for t in np.linspace(0, en.max(), 21):
+            act = ((st <= t) & (en > t))
+            heavy = act & (p[:, 10] > 0)
+            print("  t=%6.1f ms  resident CTAs %4d  (working %4d)" % (t, act.sum(), heavy.sum()))
+        order = np.argsort(st)
+        w = p[:, 10] > 0
+        print("start time of working CTAs: p50 %.1f p90 %.1f max %.1f ms; their durations p50 %.1f p90 %.1f max %.1f" % (
+            np.percentile(st[w], 50), np.percentile(st[w], 90), st[w].max(), np.percentile((en - st)[w], 50), np.percentile((en - st)[w], 90), (en - st)[w].max()))
+        last = np.argsort(-en)[:5]
+        for e in last:
+            print("  late finisher env %d: start %.1f end %.1f substeps %d sm %d" % (e, st[e], en[e], p[e, 10], p[e, 11] // 1000000))
+        sm = p[:, 11] // 1000000
+        per_sm = np.array([(en - st)[sm == k].sum() for k in range(int(sm.max()) + 1)])
+        print("busy CTA-ms per SM: min %.0f mean %.0f max %.0f (6 slots x span = %.0f)" % (per_sm.min(), per_sm.mean(), per_sm.max(), 6 * en.max()))
