@@ -424,6 +424,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                 const unsigned m = __ballot_sync(0xffffffffu, j < cnt && lstB[start + j] == first);
                 if (m) { j0 = base + __ffs(m) - 1; break; }
             }
+            if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[cnt <= 32 ? 14 : 15], (unsigned long long)(cnt - j0)); if (cnt > 32) atomicAdd((unsigned long long *)&pacc[5], 1ull); }
             if (cnt <= 32) {
                 // common case: the bucket fits the warp.  Lane l keeps member l's position in registers; the point
                 // being replayed is broadcast with shuffles, so a step costs no shared-memory round trip.
@@ -765,7 +766,7 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
         for (int j = lane; j < P.ev_words; j += 32) ev[j] = 0u;
         if (prof_on) {
             for (int o = 16; o > 0; o >>= 1) nmove += __shfl_xor_sync(0xffffffffu, nmove, o);
-            if (lane == 0) { pacc[13] += nmove; pacc[5] += 1; }
+            if (lane == 0) { pacc[13] += nmove; }
         }
     }
     // the replay warp picks the cheaper exact strategy for this substep

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     if (A.prof && tid == 0) {
         unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
         unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        c.pacc[14] = (long long)gt0; c.pacc[15] = (long long)gt1; c.pacc[11] = (long long)smid * 1000000 + c.pacc[11] % 1000000;
+        if (A.debug_flags & 2) { c.pacc[14] = (long long)gt0; c.pacc[15] = (long long)gt1; c.pacc[11] = (long long)smid * 1000000 + c.pacc[11] % 1000000; }
         c.pacc[10] = nupd;
         for (int i = 0; i < 16; i++) A.prof[(size_t)env * 16 + i] = c.pacc[i];
     }
