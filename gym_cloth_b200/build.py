@@ -16,7 +16,10 @@ LIB = os.path.join(HERE, "libclothb200.so")
 OBJ = os.path.join(HERE, "csrc", "_build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-UNITS = [("cloth_f32.cu", []), ("cloth_f64.cu", ["-fmad=false"]), ("cloth_abi.cu", [])]
+# f32 (production): flush-to-zero and approximate div/sqrt - the parity contract of this build is a tolerance, and
+# IEEE fix-up sequences around every rsqrt/division are pure latency on the serial replay paths.
+# f64 (parity): no FMA contraction, IEEE everything.
+UNITS = [("cloth_f32.cu", ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]), ("cloth_f64.cu", ["-fmad=false"]), ("cloth_abi.cu", [])]
 
 
 def _newest_src():

@@ -431,9 +431,11 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
                 const int mine = lane < cnt ? lstB[start + lane] : 0;
                 P4 Pm = pos[mine];
                 bool dirty = false;
-                for (int j = j0; j < cnt; j++) {
-                    const T pw = __shfl_sync(0xffffffffu, Pm.w, j);
-                    if (pw != T(0)) continue;
+                // pinned members never move and are skipped as subjects (cloth.pyx:314-315)
+                unsigned todo = __ballot_sync(0xffffffffu, lane < cnt && lane >= j0 && Pm.w == T(0));
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
                     const T px = __shfl_sync(0xffffffffu, Pm.x, j), py = __shfl_sync(0xffffffffu, Pm.y, j),
                             pz = __shfl_sync(0xffffffffu, Pm.z, j);
                     const T d0 = px - Pm.x, d1 = py - Pm.y, d2 = pz - Pm.z;
