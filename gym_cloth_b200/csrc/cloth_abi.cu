@@ -22,13 +22,14 @@ static thread_local std::string g_cuda_err;
 void set_cuda_error(cudaError_t e, const char *where) {
     g_cuda_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
 }
-int threads_per_cloth() {
+int threads_per_cloth(int W) {
     static int nt = [] {
         const char *s = getenv("CLOTHB200_NT");
-        int v = s ? atoi(s) : 128;
-        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 128;
+        int v = s ? atoi(s) : 0;
+        return (v == 32 || v == 64 || v == 128 || v == 256 || v == 512) ? v : 0;
     }();
-    return nt;
+    if (nt) return nt;
+    return W >= 64 ? 512 : 128;
 }
 int sweep_threshold() {
     static int v = [] { const char *s = getenv("CLOTHB200_SWEEP_THRESH"); return s ? atoi(s) : 128; }();
@@ -237,10 +238,10 @@ int clothb200_occupancy(const ClothB200Params *p, int is_f64, int *ctas_per_sm, 
     if (!p) return CLOTHB200_ERR_ARG;
     const size_t sm = is_f64 ? step_smem_f64(p) : step_smem_f32(p);
     if (smem_bytes) *smem_bytes = (int)sm;
-    if (threads) *threads = threads_per_cloth();
+    if (threads) *threads = threads_per_cloth(p->num_width_points);
     if (ctas_per_sm) {
         const int by_smem = (int)((228 * 1024) / (sm + 1024));
-        const int by_thr = 2048 / threads_per_cloth();
+        const int by_thr = 2048 / threads_per_cloth(p->num_width_points);
         int v = by_smem < by_thr ? by_smem : by_thr;
         *ctas_per_sm = v < 32 ? v : 32;
     }

@@ -65,6 +65,7 @@ template <typename T> struct DevParams {
     // of the earlier springs that share a point with s), sweep_lw entries per level: a | q << 12 | k << 24, ~0u = empty
     const uint32_t *sweep_tbl;
     int sweep_levels, sweep_lw, sweep_thresh;
+    int relax_iters;             // coloured mode: limit passes per update (>= 1; the reference does exactly one)
 };
 
 template <typename T> struct StepArgs {
@@ -143,7 +144,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define CLOTH_KEY_EMPTY 0x7fffffff
 #define CLOTH_FIRST_NONE 0x7ffffffe
 
-template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
+template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> struct ClothCTA {
     typedef typename V4<T>::type P4;
     static constexpr int NWARPS = NT / 32;
     static constexpr bool FAST = (sizeof(T) == 4);   // f32 production math; the f64 build evaluates the reference's expressions
@@ -786,6 +787,111 @@ template <typename T, int NT, int WC, bool REST_TABLE> struct ClothCTA {
     __device__ __forceinline__ void ptick(int k) {
         if (prof_on && tid == 0) { const long long t = clock64(); pacc[k] += t - plast; plast = t; }
     }
+    // ==================================================================================================
+    // Graph-coloured mode (CLOTHB200_MODE_COLOURED): same phases, but the two Gauss-Seidel passes are made parallel.
+    //  - self-collision: Jacobi - every point is corrected from the post-Verlet snapshot of its bucket (the reference
+    //    applies corrections in place in point order; the corrections carry a 1/simulation_steps factor, so the
+    //    difference is second order);
+    //  - 10 % limit: the springs are edge-coloured into 12 classes (6 kinds x 2 parity classes) whose members share no
+    //    point; classes run one after the other, all springs of a class in parallel, each on live positions.  This is
+    //    Gauss-Seidel in colour order instead of creation order.  relax_iters > 1 repeats the pass.
+    // Not bit-comparable with the reference; validated on error bounds and coverage statistics (tests/test_gpu_coloured.py).
+    // ==================================================================================================
+    static constexpr int PPT = WC ? (WC * WC + NT - 1) / NT : 1;   // points per thread (compile-time grids only)
+
+    __device__ __forceinline__ void collide_jacobi() {
+        T cx[PPT], cy[PPT], cz[PPT];
+#pragma unroll
+        for (int i = 0; i < PPT; i++) {
+            cx[i] = cy[i] = cz[i] = T(0);
+            const int p = tid + i * NT;
+            if (p >= N) continue;
+            const P4 Pp = pos[p];
+            if (Pp.w != T(0)) continue;
+            const uint32_t slot = pslot[p] & 0x7fffu;
+            if (tkey[slot] == CLOTH_FIRST_NONE) continue;          // no hit anywhere in this bucket
+            const uint32_t info = tinfo[slot];
+            const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
+            T t0 = T(0), t1 = T(0), t2 = T(0);
+            int n = 0;
+            for (int j = 0; j < cnt; j++) {                          // index order: deterministic summation
+                const int q = lstB[start + j];
+                const P4 Pq = pos[q];
+                const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+                const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                if (q != p && within_thresh(qq)) {
+                    if (qq == T(0)) { misc[3] = 1; continue; }
+                    T factor;
+                    if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                    else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                    t0 += d0 * factor; t1 += d1 * factor; t2 += d2 * factor;
+                    n += 1;
+                }
+            }
+            if (n) { const T nf = (T)n; cx[i] = t0 / nf / P.sim_steps; cy[i] = t1 / nf / P.sim_steps; cz[i] = t2 / nf / P.sim_steps; }
+        }
+        sync();   // every point has read the snapshot
+#pragma unroll
+        for (int i = 0; i < PPT; i++) {
+            const int p = tid + i * NT;
+            if (p >= N) continue;
+            const P4 Pp = pos[p];
+            if (Pp.w != T(0)) continue;
+            if (cx[i] != T(0) || cy[i] != T(0) || cz[i] != T(0)) pos[p] = mk4(Pp.x + cx[i], Pp.y + cy[i], Pp.z + cz[i], Pp.w);
+            plane_point(p);
+        }
+    }
+
+    // one colour class: kind k, parity par (of r for k = 0,2,3; of c for k = 1; of r/2 for k = 4; of c/2 for k = 5)
+    __device__ __forceinline__ void limit_colour(int k, int par) {
+        const int off = koff(k);
+        for (int p = tid; p < N; p += NT) {
+            const int r = p / W, c = p - r * W;
+            const int key = (k == 1) ? c : (k == 4 ? (r >> 1) : (k == 5 ? (c >> 1) : r));
+            if ((key & 1) != par || !kvalid(r, c, k)) continue;
+            const int a = p - off;
+            const P4 Pa = pos[a], Pb = pos[p];
+            const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
+            if (pa && pb) continue;
+            const T rst = rest_of(p, k);
+            const T e0 = Pa.x - Pb.x, e1 = Pa.y - Pb.y, e2 = Pa.z - Pb.z;
+            const T c11 = rst * T(1.1);
+            const T qd = e0 * e0 + e1 * e1 + e2 * e2;
+            const T ct = rst * P.tear_thresh;
+            if (qd > ct * ct) misc[2] = 1;
+            if (qd > c11 * c11) {
+                T fac;
+                if (FAST) fac = T(1) - c11 * rsqrtf((float)qd);
+                else { const T l = sqrt_t(qd); fac = (l - c11) / l; }
+                const T fa = pa ? T(0) : (pb ? fac : fac * T(0.5));
+                const T fb = pb ? T(0) : (pa ? fac : fac * T(0.5));
+                if (!pa) pos[a] = mk4(Pa.x - e0 * fa, Pa.y - e1 * fa, Pa.z - e2 * fa, Pa.w);
+                if (!pb) pos[p] = mk4(Pb.x + e0 * fb, Pb.y + e1 * fb, Pb.z + e2 * fb, Pb.w);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void update_coloured() {
+        if (prof_on && tid == 0) plast = clock64();
+        hooke_verlet();            sync(); ptick(0);
+        commit_and_hash();         sync(); ptick(1);
+        alloc_buckets();           sync(); ptick(2);
+        scatter_members();         sync(); ptick(3);
+        order_and_snapshot();      sync(); ptick(4);
+        collide_jacobi();          sync(); ptick(6);
+        for (int j = tid; j < P.table_size; j += NT) { tkey[j] = CLOTH_KEY_EMPTY; tinfo[j] = 0u; }
+        for (int it = 0; it < P.relax_iters; it++) {
+            for (int k = 0; k < 6; k++) {
+                limit_colour(k, 0); sync();
+                limit_colour(k, 1); sync();
+            }
+        }
+        if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+        sync(); ptick(8);
+    }
+
+    __device__ __forceinline__ void update() { if (COLOURED) update_coloured(); else update_reference_order(); }
+
     // ---- one Cloth.update() (cloth.pyx:169-214), reference order ----
     __device__ __forceinline__ void update_reference_order() {
         if (prof_on && tid == 0) plast = clock64();

@@ -16,9 +16,9 @@ void set_cuda_error(cudaError_t e, const char *where);
 // ------------------------------------------------------------------------------------------------
 // The action kernel: one CTA = one cloth = one whole ClothEnv.step (or n bare updates).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int WC, bool REST_TABLE>
+template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED>
 __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ DevParams<T> P, const __grid_constant__ StepArgs<T> A) {
-    typedef ClothCTA<T, NT, WC, REST_TABLE> CTA;
+    typedef ClothCTA<T, NT, WC, REST_TABLE, COLOURED> CTA;
     typedef typename CTA::P4 P4;
     extern __shared__ __align__(128) unsigned char smem[];
     const int env = A.env_order ? A.env_order[blockIdx.x] : (int)blockIdx.x;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
             else if (i < e3) { }
             else if (!released) { c.gripper_release(); released = true; c.sync(); }
         }
-        c.update_reference_order();
+        c.update();
         nupd++;
         if (stepping && c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
     }
@@ -330,13 +330,14 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     P.iu = hp.iters_up; P.iur = hp.iters_up_rest; P.igr = hp.iters_grip_rest; P.ir = hp.iters_rest;
     P.sweep_tbl = get_sweep_table(W, &P.sweep_levels, &P.sweep_lw);
     P.sweep_thresh = sweep_threshold();
+    P.relax_iters = hp.reserved0 > 1 ? hp.reserved0 : 1;
     return 0;
 }
 
-template <typename T, int NT, int WC, bool RT> int launch_step_inst(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
-    typedef ClothCTA<T, NT, WC, RT> CTA;
+template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
+    typedef ClothCTA<T, NT, WC, RT, COL> CTA;
     const size_t smem = CTA::smem_bytes(P.N, P.table_size, P.ev_words);
-    auto kern = cloth_step_kernel<T, NT, WC, RT>;
+    auto kern = cloth_step_kernel<T, NT, WC, RT, COL>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -350,36 +351,54 @@ template <typename T, int NT, int WC, bool RT> int launch_step_inst(const DevPar
     return CLOTHB200_OK;
 }
 
-int threads_per_cloth();   // cloth_abi.cu: CLOTHB200_NT env var, default 128
+int threads_per_cloth(int W);   // cloth_abi.cu: CLOTHB200_NT env var; default 128 (512 for 64x64)
 
-template <typename T, int WC, bool RT> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
-    switch (threads_per_cloth()) {
-        case 32: return launch_step_inst<T, 32, WC, RT>(P, A, st);
-        case 64: return launch_step_inst<T, 64, WC, RT>(P, A, st);
-        case 256: return launch_step_inst<T, 256, WC, RT>(P, A, st);
-        default: return launch_step_inst<T, 128, WC, RT>(P, A, st);
+template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
+    const int nt = threads_per_cloth(P.W);
+    if (WC == 64) {   // one resident cloth per SM: wide CTAs
+        if (nt == 256) return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
+        return launch_step_inst<T, 512, WC, RT, COL>(P, A, st);
+    }
+    if (COL) {        // the coloured mode has no single-warp phases: two sizes are enough
+        if (nt == 256) return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
+        return launch_step_inst<T, 128, WC, RT, COL>(P, A, st);
+    }
+    switch (nt) {
+        case 32: return launch_step_inst<T, 32, WC, RT, COL>(P, A, st);
+        case 64: return launch_step_inst<T, 64, WC, RT, COL>(P, A, st);
+        case 256: return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
+        default: return launch_step_inst<T, 128, WC, RT, COL>(P, A, st);
     }
 }
 
-template <typename T> int launch_step(const ClothB200Params &hp, const StepArgs<T> &A, cudaStream_t st) {
+template <typename T> int launch_step(const ClothB200Params &hp, const StepArgs<T> &A, cudaStream_t st, int rmode = 0) {
     if (A.n_env == 0) return CLOTHB200_OK;
     DevParams<T> P;
     make_dev_params(hp, P);
     if (P.N >= 32768) return CLOTHB200_ERR_UNSUPPORTED;   // 15-bit slots / 16-bit indices
     const bool rt = A.rest != nullptr;
-    if (!rt && sizeof(T) == 8) return CLOTHB200_ERR_ARG;  // the parity build always takes the exact rest table
-    if (P.W == 25 && P.H == 25) {
-        if (rt) return launch_step_nt<T, 25, true>(P, A, st);
-        return launch_step_nt<T, 25, false>(P, A, st);
+    if (!rt && sizeof(T) == 8 && rmode == 0) return CLOTHB200_ERR_ARG;  // the parity build always takes the exact rest table
+    if (rmode == CLOTHB200_MODE_COLOURED) {
+        if (P.W == 25 && P.H == 25) return rt ? launch_step_nt<T, 25, true, true>(P, A, st) : launch_step_nt<T, 25, false, true>(P, A, st);
+        if (P.W == 64 && P.H == 64) return rt ? launch_step_nt<T, 64, true, true>(P, A, st) : launch_step_nt<T, 64, false, true>(P, A, st);
+        return CLOTHB200_ERR_UNSUPPORTED;   // coloured mode is built for the 25x25 and 64x64 grids
     }
-    if (rt) return launch_step_nt<T, 0, true>(P, A, st);
-    return launch_step_nt<T, 0, false>(P, A, st);
+    if (P.W == 25 && P.H == 25) {
+        if (rt) return launch_step_nt<T, 25, true, false>(P, A, st);
+        return launch_step_nt<T, 25, false, false>(P, A, st);
+    }
+    if (P.W == 64 && P.H == 64) {
+        if (rt) return launch_step_nt<T, 64, true, false>(P, A, st);
+        return launch_step_nt<T, 64, false, false>(P, A, st);
+    }
+    if (rt) return launch_step_nt<T, 0, true, false>(P, A, st);
+    return launch_step_nt<T, 0, false, false>(P, A, st);
 }
 
 template <typename T> size_t step_smem_bytes(const ClothB200Params &hp) {
     DevParams<T> P;
     make_dev_params(hp, P);
-    return ClothCTA<T, 128, 0, true>::smem_bytes(P.N, P.table_size, P.ev_words);
+    return ClothCTA<T, 128, 0, true, false>::smem_bytes(P.N, P.table_size, P.ev_words);
 }
 
 }  // namespace clothb200

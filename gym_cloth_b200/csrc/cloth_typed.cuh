@@ -40,7 +40,7 @@ int step_plans_t(const ClothB200Params *hp, int mode, int n_env, const ClothB200
     int rc = check_io<T>(n_env, io);
     if (rc || n_env == 0) return rc;
     if (!hp || !plans) return CLOTHB200_ERR_ARG;
-    if (mode != CLOTHB200_MODE_REFERENCE_ORDER) return CLOTHB200_ERR_UNSUPPORTED;
+    if (mode != CLOTHB200_MODE_REFERENCE_ORDER && mode != CLOTHB200_MODE_COLOURED) return CLOTHB200_ERR_UNSUPPORTED;
     StepArgs<T> A = make_args<T>(n_env, io);
     A.plans = plans; A.mode = KMODE_STEP; A.initialize = initialize;
     if (!io->env_order && io->sched_scratch && n_env > 1 && n_env <= 65536) {
@@ -59,7 +59,7 @@ int step_plans_t(const ClothB200Params *hp, int mode, int n_env, const ClothB200
         if (e != cudaSuccess) { set_cuda_error(e, "schedule kernels"); return CLOTHB200_ERR_CUDA; }
         A.env_order = order;
     }
-    return launch_step<T>(*hp, A, st);
+    return launch_step<T>(*hp, A, st, mode);
 }
 
 template <typename T>
@@ -67,10 +67,10 @@ int update_n_t(const ClothB200Params *hp, int mode, int n_env, int n_updates, co
     int rc = check_io<T>(n_env, io);
     if (rc || n_env == 0) return rc;
     if (!hp || n_updates < 0) return CLOTHB200_ERR_ARG;
-    if (mode != CLOTHB200_MODE_REFERENCE_ORDER) return CLOTHB200_ERR_UNSUPPORTED;
+    if (mode != CLOTHB200_MODE_REFERENCE_ORDER && mode != CLOTHB200_MODE_COLOURED) return CLOTHB200_ERR_UNSUPPORTED;
     StepArgs<T> A = make_args<T>(n_env, io);
     A.mode = KMODE_UPDATE; A.n_updates = n_updates;
-    return launch_step<T>(*hp, A, st);
+    return launch_step<T>(*hp, A, st, mode);
 }
 
 template <typename T>

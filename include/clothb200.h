@@ -72,7 +72,8 @@ typedef struct ClothB200Params {
     int32_t iters_pull_max, max_actions;
     double reduce_factor, grip_radius, gripper_height;
     int32_t clip_act_space, delta_actions;
-    int32_t force_grab, reserved0;
+    int32_t force_grab;
+    int32_t reserved0;                           /* coloured mode: limit passes per update (relax_iters); 0/1 = one pass */
 } ClothB200Params;
 
 /* One decoded pull action (cloth_env.py:401-470): where to grip, the per-substep pull delta and

@@ -11,7 +11,11 @@ def actions(rng, n):
 
 def timed_action(n, dtype, seed=0, reps=2):
     rng = np.random.RandomState(seed)
-    bc = BatchedCloth(L.default_params(), n, dtype=dtype)
+    P = L.default_params()
+    if os.environ.get("W64"):
+        P.num_width_points = P.num_height_points = 64; P.thickness = 0.006
+    P.reserved0 = int(os.environ.get("RELAX", "1"))
+    bc = BatchedCloth(P, n, dtype=dtype, mode=int(os.environ.get("MODE", "0")))
     bc.schedule = os.environ.get("NOSCHED") is None
     a0 = torch.from_numpy(actions(rng, n)).to("cuda", dtype)
     bc.step_actions(a0); torch.cuda.synchronize()          # crumple (untimed)
@@ -23,7 +27,7 @@ def timed_action(n, dtype, seed=0, reps=2):
         ms = e0.elapsed_time(e1); sub = int(bc.sim_steps.sum().item())
         per_env_ms = (bc.cost.double() * bc.sim_steps.double() / 1.965e6).cpu().numpy()
         print("   per-env busy time: max %.1f ms, p99 %.1f, mean(active) %.1f; sum/slots(888) %.1f ms; kernel %.1f ms" % (
-            per_env_ms.max(), np.percentile(per_env_ms, 99), per_env_ms[per_env_ms > 0].mean(), per_env_ms.sum() / 888, ms))
+            per_env_ms.max(), np.percentile(per_env_ms, 99), per_env_ms[per_env_ms > 0].mean(), per_env_ms.sum() / 888, ms)) if not os.environ.get('QUIET') else None
         res.append((ms, sub, sub / ms * 1e3, n / ms * 1e3, int(((bc.flags & 4) != 0).sum().item())))
     return res, bc
 
