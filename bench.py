@@ -242,11 +242,32 @@ def run_ours(args):
                              "frac": (n * K / (kernel_ms * 1e-3)) * HBM_B_PER_ENV_STEP / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src},
             "mean_coverage": float(cov_stats[0].item() / cov_stats[1].item()),
         }
+        if world == 1 and not args.no_extras:
+            line["other_builds"] = other_builds(args, pool, dev_actions[W:W + 2])
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(env, pool, args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_builds(args, pool, actions):
+    """Same workload, two steps each, for the other two builds of the kernel (reported beside the headline):
+    graph-coloured f32 and reference-order f64 (the bit-exact parity build)."""
+    import torch
+    from gym_cloth_b200 import lib as L
+    from gym_cloth_b200.batched import BatchedCloth
+    out = {}
+    for name, dt, mode in (("coloured_f32", torch.float32, L.MODE_COLOURED), ("reference_order_f64", torch.float64, L.MODE_REFERENCE_ORDER)):
+        bc = BatchedCloth(L.default_params(), args.envs, dtype=dt, mode=mode)
+        bc.pos.copy_(pool["pos"].to(dt)); bc.prev.copy_(pool["prev"].to(dt))
+        bc.step_actions(actions[0].to(dt)); torch.cuda.synchronize()        # warm-up (also makes states diverge from the pool)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); bc.step_actions(actions[1].to(dt)); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[name] = {"env_steps_per_s": args.envs / (ms * 1e-3), "substeps_per_s": float(bc.sim_steps.sum().item()) / (ms * 1e-3),
+                     "ms_per_step": ms, "steps": 1, "warmup": 1}
+    return out
 
 
 def _pool_states(pool, k):
@@ -331,6 +352,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

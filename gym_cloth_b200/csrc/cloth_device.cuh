@@ -366,18 +366,27 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             if (cnt > 1) {
                 const P4 Pp = pos[p];
                 int first = CLOTH_FIRST_NONE;
-                for (int j = 0; j < cnt; j++) {
-                    const int q = lstA[start + j];
-                    rk += (q < p) ? 1 : 0;
-                    if (q > p) {
-                        const P4 Pq = pos[q];
-                        const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-                        if (within_thresh(d0 * d0 + d1 * d1 + d2 * d2)) {
-                            const int h = Pp.w == T(0) ? p : (Pq.w == T(0) ? q : CLOTH_FIRST_NONE);
-                            first = h < first ? h : first;
-                        }
-                    }
+                // a hit makes every unpinned end of the pair a hit point; the pair is tested by its lower index
+#define CLOTH_PAIR(q, Q)                                                                                    \
+    {                                                                                                       \
+        const T d0 = Pp.x - Q.x, d1 = Pp.y - Q.y, d2 = Pp.z - Q.z;                                          \
+        const bool hit = q > p && within_thresh(d0 * d0 + d1 * d1 + d2 * d2);                               \
+        const int h = Pp.w == T(0) ? p : (Q.w == T(0) ? q : CLOTH_FIRST_NONE);                              \
+        first = (hit && h < first) ? h : first;                                                             \
+        rk += (q < p) ? 1 : 0;                                                                              \
+    }
+                int j = 0;
+                for (; j + 4 <= cnt; j += 4) {      // four candidates in flight: index and position loads overlap
+                    const int q0 = lstA[start + j], q1 = lstA[start + j + 1], q2 = lstA[start + j + 2], q3 = lstA[start + j + 3];
+                    const P4 Q0 = pos[q0], Q1 = pos[q1], Q2 = pos[q2], Q3 = pos[q3];
+                    CLOTH_PAIR(q0, Q0) CLOTH_PAIR(q1, Q1) CLOTH_PAIR(q2, Q2) CLOTH_PAIR(q3, Q3)
                 }
+                for (; j < cnt; j++) {
+                    const int q0 = lstA[start + j];
+                    const P4 Q0 = pos[q0];
+                    CLOTH_PAIR(q0, Q0)
+                }
+#undef CLOTH_PAIR
                 if (first != CLOTH_FIRST_NONE) atomicMin(&tkey[slot], first);
             }
             lstB[start + rk] = (uint16_t)p;
@@ -814,20 +823,33 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
             T t0 = T(0), t1 = T(0), t2 = T(0);
             int n = 0;
-            for (int j = 0; j < cnt; j++) {                          // index order: deterministic summation
-                const int q = lstB[start + j];
-                const P4 Pq = pos[q];
-                const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-                const T qq = d0 * d0 + d1 * d1 + d2 * d2;
-                if (q != p && within_thresh(qq)) {
-                    if (qq == T(0)) { misc[3] = 1; continue; }
-                    T factor;
-                    if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
-                    else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
-                    t0 += d0 * factor; t1 += d1 * factor; t2 += d2 * factor;
-                    n += 1;
-                }
+#define CLOTH_JAC(q, Pq)                                                                                    \
+    {                                                                                                       \
+        const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;                                       \
+        const T qq = d0 * d0 + d1 * d1 + d2 * d2;                                                           \
+        if (q != p && within_thresh(qq)) {                                                                  \
+            if (qq == T(0)) misc[3] = 1;                                                                    \
+            else {                                                                                          \
+                T factor;                                                                                   \
+                if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);                                     \
+                else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }                               \
+                t0 += d0 * factor; t1 += d1 * factor; t2 += d2 * factor;                                    \
+                n += 1;                                                                                     \
+            }                                                                                               \
+        }                                                                                                   \
+    }
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {                           // index order: deterministic summation
+                const int q0 = lstB[start + j], q1 = lstB[start + j + 1], q2 = lstB[start + j + 2], q3 = lstB[start + j + 3];
+                const P4 Q0 = pos[q0], Q1 = pos[q1], Q2 = pos[q2], Q3 = pos[q3];
+                CLOTH_JAC(q0, Q0) CLOTH_JAC(q1, Q1) CLOTH_JAC(q2, Q2) CLOTH_JAC(q3, Q3)
             }
+            for (; j < cnt; j++) {
+                const int q0 = lstB[start + j];
+                const P4 Q0 = pos[q0];
+                CLOTH_JAC(q0, Q0)
+            }
+#undef CLOTH_JAC
             if (n) { const T nf = (T)n; cx[i] = t0 / nf / P.sim_steps; cy[i] = t1 / nf / P.sim_steps; cz[i] = t2 / nf / P.sim_steps; }
         }
         sync();   // every point has read the snapshot
@@ -843,7 +865,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     }
 
     // one colour class: kind k, parity par (of r for k = 0,2,3; of c for k = 1; of r/2 for k = 4; of c/2 for k = 5)
-    __device__ __forceinline__ void limit_colour(int k, int par) {
+    template <int k, int par> __device__ __forceinline__ void limit_colour() {
         const int off = koff(k);
         for (int p = tid; p < N; p += NT) {
             const int r = p / W, c = p - r * W;
@@ -881,10 +903,12 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         collide_jacobi();          sync(); ptick(6);
         for (int j = tid; j < P.table_size; j += NT) { tkey[j] = CLOTH_KEY_EMPTY; tinfo[j] = 0u; }
         for (int it = 0; it < P.relax_iters; it++) {
-            for (int k = 0; k < 6; k++) {
-                limit_colour(k, 0); sync();
-                limit_colour(k, 1); sync();
-            }
+            limit_colour<0, 0>(); sync(); limit_colour<0, 1>(); sync();
+            limit_colour<1, 0>(); sync(); limit_colour<1, 1>(); sync();
+            limit_colour<2, 0>(); sync(); limit_colour<2, 1>(); sync();
+            limit_colour<3, 0>(); sync(); limit_colour<3, 1>(); sync();
+            limit_colour<4, 0>(); sync(); limit_colour<4, 1>(); sync();
+            limit_colour<5, 0>(); sync(); limit_colour<5, 1>(); sync();
         }
         if (tid == 0) { misc[0] = 0; misc[1] = 0; }
         sync(); ptick(8);

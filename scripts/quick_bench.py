@@ -61,7 +61,7 @@ if __name__ == "__main__":
         import ctypes as C
         dt = torch.float32 if (len(sys.argv) < 4 or sys.argv[3] == "f32") else torch.float64
         rng = np.random.RandomState(0)
-        bc = BatchedCloth(L.default_params(), n, dtype=dt)
+        bc = BatchedCloth(L.default_params(), n, dtype=dt, mode=int(os.environ.get("MODE", "0")))
         a0 = torch.from_numpy(actions(rng, n)).to("cuda", dt)
         bc.step_actions(a0); torch.cuda.synchronize()
         prof = torch.zeros(n, 16, dtype=torch.int64, device="cuda")
