@@ -66,6 +66,7 @@ template <typename T> struct DevParams {
     const uint32_t *sweep_tbl;
     int sweep_levels, sweep_lw, sweep_thresh;
     int relax_iters;             // coloured mode: limit passes per update (>= 1; the reference does exactly one)
+    int force_grab;              // cfg env.force_grab: grow the grip radius by 0.02 until something is gripped (cloth_env.py:434-444)
 };
 
 template <typename T> struct StepArgs {

@@ -64,6 +64,13 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     if (stepping) {
         const ClothB200Plan plan = A.plans[env];
         ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
+        if (P.force_grab) {
+            // cloth_env.py:434-444: `while len(grabbed_pts) == 0: grip_radius += 0.02; grab_top(...)` (radius restored afterwards).
+            // A cloth with no point under z = height + 2*thickness can never be gripped; the reference would spin forever,
+            // we stop once the cylinder covers any reachable (x, y) and report NOGRAB.
+            double rad = P.grip_radius;
+            for (int tries = 0; ngrab == 0 && tries < 4096; tries++) { rad += 0.02; ngrab = c.grab_top(plan.gx, plan.gy, rad); }
+        }
         if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
         // _pull thresholds (cloth_env.py:352-367, 472-475): `i < t` for integer i <=> i < ceil(t)
         const double iu = A.iters_up_env ? A.iters_up_env[env] : P.iu;
@@ -331,6 +338,7 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     P.sweep_tbl = get_sweep_table(W, &P.sweep_levels, &P.sweep_lw);
     P.sweep_thresh = sweep_threshold();
     P.relax_iters = hp.reserved0 > 1 ? hp.reserved0 : 1;
+    P.force_grab = hp.force_grab ? 1 : 0;
     return 0;
 }
 
