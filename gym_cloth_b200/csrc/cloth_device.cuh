@@ -424,7 +424,11 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // own evaluation equals the snapshot), in index order; contributions are summed in candidate order.
     __device__ __forceinline__ void collide_replay() {
         const int nwork = misc[1];
-        for (int wi = (warp + NWARPS - rot % NWARPS) % NWARPS; wi < nwork; wi += NWARPS) {
+        for (;;) {
+            int wi = 0;
+            if (lane == 0) wi = atomicAdd(&misc[6], 1);     // buckets are handed out dynamically: their sizes vary a lot
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            if (wi >= nwork) break;
             const uint32_t slot = lstA[wi];
             const uint32_t info = tinfo[slot];
             const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
@@ -555,6 +559,9 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // snapshot test of all springs; also clears the hash table for the next substep
     __device__ __forceinline__ void limit_snapshot() {
         for (int j = tid; j < P.table_size; j += NT) { tkey[j] = CLOTH_KEY_EMPTY; tinfo[j] = 0u; }
+        // the previous substep swept and still shortened many springs: the sweep is exact whatever the flags say,
+        // so the flag pass is skipped until a sweep comes back short
+        if (misc[7]) return;
         for (int p = tid; p < N; p += NT) {
             const P4 Pb = pos[p];
             const int r = p / W, c = p - r * W;
@@ -777,15 +784,17 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             for (int u = 0; u < 8; u++) { cur[u] = nxt[u]; rcur[u] = rnxt[u]; }
         }
         for (int j = lane; j < P.ev_words; j += 32) ev[j] = 0u;
-        if (prof_on) {
-            for (int o = 16; o > 0; o >>= 1) nmove += __shfl_xor_sync(0xffffffffu, nmove, o);
-            if (lane == 0) { pacc[13] += nmove; }
+        nmove = __reduce_add_sync(0xffffffffu, nmove);
+        if (lane == 0) {
+            misc[7] = nmove >= P.sweep_thresh ? 1 : 0;
+            if (prof_on) pacc[13] += nmove;
         }
     }
     // the replay warp picks the cheaper exact strategy for this substep
     __device__ __forceinline__ void limit_resolve(int replay_warp) {
         if (warp != replay_warp) return;
         if (P.sweep_tbl != nullptr) {
+            if (misc[7]) { limit_sweep(); return; }
             int cnt = 0;
             for (int j = lane; j < P.ev_words; j += 32) cnt += __popc(ev[j]);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -911,7 +920,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             limit_colour<4, 0>(); sync(); limit_colour<4, 1>(); sync();
             limit_colour<5, 0>(); sync(); limit_colour<5, 1>(); sync();
         }
-        if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+        if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[6] = 0; }
         sync(); ptick(8);
     }
 
@@ -930,7 +939,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         collide_replay();          sync(); ptick(7);
         limit_snapshot();          sync(); ptick(8);
         limit_resolve(rot % NWARPS);
-        if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+        if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[6] = 0; }
         sync(); ptick(9);
     }
 
