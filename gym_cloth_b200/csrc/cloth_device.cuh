@@ -175,17 +175,21 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         prev = reinterpret_cast<P4 *>(smem + o); o += sizeof(P4) * (size_t)N;
         tkey = reinterpret_cast<int *>(smem + o); o += 4 * (size_t)P.table_size;
         tinfo = reinterpret_cast<uint32_t *>(smem + o); o += 4 * (size_t)P.table_size;
-        ev = reinterpret_cast<uint32_t *>(smem + o); o += 4 * (size_t)((P.ev_words + 3) & ~3);
         misc = reinterpret_cast<int *>(smem + o); o += 4 * 16;
         pacc = reinterpret_cast<long long *>(smem + o); o += 8 * 16;
         kc = reinterpret_cast<float2 *>(smem + o); o += 8 * 8;
-        pslot = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
+        // the stretched-spring queue `ev` shares its storage with `pslot`: pslot is dead once the collision replay
+        // starts (which zeroes the area), ev lives from the limit snapshot to the end of the update
+        const size_t ps_bytes = 2 * (size_t)((N + 7) & ~7), ev_bytes = 4 * (size_t)((P.ev_words + 3) & ~3);
+        pslot = reinterpret_cast<uint16_t *>(smem + o);
+        ev = reinterpret_cast<uint32_t *>(smem + o); o += ps_bytes > ev_bytes ? ps_bytes : ev_bytes;
         lstA = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
         lstB = reinterpret_cast<uint16_t *>(smem + o); o += 2 * (size_t)((N + 7) & ~7);
     }
     static __host__ __device__ size_t smem_bytes(int N, int table_size, int ev_words) {
-        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 4 * (size_t)((ev_words + 3) & ~3) + 64 + 128 + 64 +
-               3 * 2 * (size_t)((N + 7) & ~7) + 16 /* mbarrier */;
+        const size_t ps_bytes = 2 * (size_t)((N + 7) & ~7), ev_bytes = 4 * (size_t)((ev_words + 3) & ~3);
+        return sizeof(P4) * (size_t)N * 2 + 8 * (size_t)table_size + 64 + 128 + 64 + (ps_bytes > ev_bytes ? ps_bytes : ev_bytes) +
+               2 * ps_bytes + 16 /* mbarrier */;
     }
 
     __device__ __forceinline__ void sync() {
@@ -321,13 +325,15 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                             cell(Pp.z, P.cell_t, P.inv_cell_t);
             uint32_t slot = ((uint32_t)key * 2654435761u) >> P.table_shift;
             const uint32_t msk = (uint32_t)P.table_size - 1;
-            for (;;) {
+            for (int probes = 0;; probes++) {
                 int old = *reinterpret_cast<volatile int *>(&tkey[slot]);
                 if (old == key) break;
                 if (old == CLOTH_KEY_EMPTY) {
                     old = atomicCAS(&tkey[slot], CLOTH_KEY_EMPTY, key);
                     if (old == CLOTH_KEY_EMPTY || old == key) break;
                 }
+                // more occupied cells than table slots (> 3x the cells of the flat cloth): not a cloth any more
+                if (probes > (int)msk) { misc[3] = 1; break; }
                 slot = (slot + 1) & msk;
             }
             const uint32_t r = atomicAdd(&tinfo[slot], 1u);
@@ -423,6 +429,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // ordered replay of one bucket by one warp: from the first hit point on (nothing before it moved, so its
     // own evaluation equals the snapshot), in index order; contributions are summed in candidate order.
     __device__ __forceinline__ void collide_replay() {
+        for (int j = tid; j < P.ev_words; j += NT) ev[j] = 0u;   // pslot is dead from here on: its storage becomes the spring queue
         const int nwork = misc[1];
         for (;;) {
             int wi = 0;
@@ -1047,8 +1054,8 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // Andrew monotone chain + shoelace in double, same operation order as oracle_hull_area.
     // Uses the hash table area as scratch (the table is rebuilt from scratch every substep).
     __device__ __forceinline__ double hull_area() {
-        uint16_t *idx = reinterpret_cast<uint16_t *>(tkey);   // [np2]
-        uint16_t *hull = reinterpret_cast<uint16_t *>(tinfo); // [2N]
+        uint16_t *idx = reinterpret_cast<uint16_t *>(tkey);   // [np2] spans tkey+tinfo (8*table_size bytes, table_size >= np2/4)
+        uint16_t *hull = lstA;                                // [2N] spans lstA+lstB (contiguous, idle outside update())
         int np2 = 1; while (np2 < N) np2 <<= 1;
         for (int i = tid; i < np2; i += NT) idx[i] = (uint16_t)i;
         sync();

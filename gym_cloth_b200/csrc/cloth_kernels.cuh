@@ -297,7 +297,10 @@ int sweep_threshold();
 template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T> &P) {
     const int W = hp.num_width_points, H = hp.num_height_points;
     P.W = W; P.H = H; P.N = W * H;
-    int ts = 64; while (ts < (P.N * 8 + 4) / 5) ts <<= 1;   // >= 1.6 N
+    // hash table slots: 3x the cells a flat cloth occupies (cell = 3 grid spacings; oracle runs never exceeded 1.15x)
+    const int cells = (W + 2) / 3 + 1;
+    int ts = 64; while (ts < 3 * cells * cells) ts <<= 1;
+    { int np2 = 1; while (np2 < P.N) np2 <<= 1; while (4 * ts < np2) ts <<= 1; }   // the coverage sort borrows the table area
     P.table_size = ts;
     int sh = 0; while ((1 << sh) < ts) sh++;
     P.table_shift = 32 - sh;
@@ -332,7 +335,7 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     for (int k = 0; k < 6; k++) P.rest_k[k] = (T)rk[k];
     P.grip_radius = hp.grip_radius; P.thickness = hp.thickness; P.gripper_height = hp.gripper_height;
     int nlev = 0;
-    for (double z = hp.gripper_height; z > 0; z -= hp.thickness) { nlev++; if (nlev > 4 * ts / 8) break; }
+    for (double z = hp.gripper_height; z > 0; z -= hp.thickness) { nlev++; if (nlev > 8 * ts / 8) break; }
     P.n_levels = nlev;
     P.iu = hp.iters_up; P.iur = hp.iters_up_rest; P.igr = hp.iters_grip_rest; P.ir = hp.iters_rest;
     P.sweep_tbl = get_sweep_table(W, &P.sweep_levels, &P.sweep_lw);
