@@ -80,4 +80,5 @@ def load_env(reference="/root/reference"):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from gym_cloth.envs.cloth_env import ClothEnv
+    sys.modules["gym_cloth.envs"].ClothEnv = ClothEnv   # what gym_cloth/envs/__init__.py exports
     return ClothEnv

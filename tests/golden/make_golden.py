@@ -253,6 +253,38 @@ def gen_env(out, tier, seed, n_actions, action_seed=None):
     np.savez_compressed(os.path.join(out, "env_t%d_s%d.npz" % (tier, seed)), **d)
 
 
+def gen_policy(out, tier=1, seed=1337, episodes=2):
+    """BASELINE config #1: the reference's own OracleCornerPolicy (examples/analytic.py:70-155) driving the reference
+    ClothEnv, tier 1.  Records every action the policy chose and what the env returned."""
+    sys.path.insert(0, os.path.join(REFERENCE, "examples"))
+    tmp = tempfile.mkdtemp(prefix="golden_pol_")
+    env = _make_env(tier, seed, tmp)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import analytic
+    policy = analytic.OracleCornerPolicy()
+    policy.set_env_cfg(env, env.cfg)
+    d = {"tier": tier, "seed": seed}
+    ep_len = []
+    k = 0
+    for ep in range(episodes):
+        obs = env.reset()
+        d["pos_reset_e%d" % ep] = _state(env.cloth)[0]
+        d["start_coverage_e%d" % ep] = env._start_coverage
+        done = False; t = 0
+        while not done:
+            with contextlib.redirect_stdout(io.StringIO()):
+                a = policy.get_action(obs, t)
+            obs, rew, done, info = env.step(a)
+            d["action_%d" % k] = np.array([float(v) for v in a]); d["pos_%d" % k] = _state(env.cloth)[0]
+            d["result_%d" % k] = np.array([rew, float(done), info["actual_coverage"], info["num_sim_steps"]])
+            print("policy ep %d t %d: action %s cov %.4f rew %.3f done %s" % (ep, t, np.round(a, 3), info["actual_coverage"], rew, done))
+            k += 1; t += 1
+        ep_len.append(t)
+    d["episode_lengths"] = np.array(ep_len)
+    np.savez_compressed(os.path.join(out, "policy_oracle_t%d_s%d.npz" % (tier, seed)), **d)
+
+
 def gen_decode(out):
     """Action decode exactly as ClothEnv.step computes it (cloth_env.py:401-475), captured by
     hooking gripper.grab_top and _pull with the physics update stubbed out."""
@@ -338,7 +370,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -352,12 +384,12 @@ def main():
                 ["env", "--tier", "1", "--seed", "1337", "--actions", "3"],
                 ["env", "--tier", "1", "--seed", "1338", "--actions", "3"],
                 ["env", "--tier", "2", "--seed", "1337", "--actions", "2"],
-                ["env", "--tier", "3", "--seed", "1337", "--actions", "2"]]
+                ["env", "--tier", "3", "--seed", "1337", "--actions", "2"], ["policy"]]
         procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__)] + j + ["--out", a.out]) for j in jobs]
         rc = [p.wait() for p in procs]
         print("exit codes", rc)
         sys.exit(max(rc))
-    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear}.get(
+    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy}.get(
         a.what, lambda out: gen_env(out, a.tier, a.seed, a.actions))(a.out)
 
 
