@@ -26,8 +26,8 @@ def timed_action(n, dtype, seed=0, reps=2):
         e0.record(); bc.step_actions(a); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1); sub = int(bc.sim_steps.sum().item())
         per_env_ms = (bc.cost.double() * bc.sim_steps.double() / 1.965e6).cpu().numpy()
-        print("   per-env busy time: max %.1f ms, p99 %.1f, mean(active) %.1f; sum/slots(888) %.1f ms; kernel %.1f ms" % (
-            per_env_ms.max(), np.percentile(per_env_ms, 99), per_env_ms[per_env_ms > 0].mean(), per_env_ms.sum() / 888, ms)) if not os.environ.get('QUIET') else None
+        print("   per-env busy time: max %.1f ms, p99 %.1f, mean(active) %.1f; sum/slots(1184) %.1f ms; kernel %.1f ms" % (
+            per_env_ms.max(), np.percentile(per_env_ms, 99), per_env_ms[per_env_ms > 0].mean(), per_env_ms.sum() / 1184, ms)) if not os.environ.get('QUIET') else None
         res.append((ms, sub, sub / ms * 1e3, n / ms * 1e3, int(((bc.flags & 4) != 0).sum().item())))
     return res, bc
 
