@@ -95,6 +95,35 @@ if __name__ == "__main__":
             ns = p[e, 10]
             print("  %4d %8d %11.0f %9.1f %9.1f %12.0f %12.1f %12.0f" % (e, ns, p[e, :10].sum() / ns, p[e, 12] / ns, p[e, 13] / ns,
                   p[e, 9] / max(p[e, 12], 1), p[e, 11] / ns, p[e, 7] / max(p[e, 11], 1)))
+    elif what == "sched":
+        # how much of the launch time is mis-prediction? run the same action from the same state three ways:
+        # predicted costs (what a user gets), exact costs (from the first run), no scheduling
+        dt = torch.float32
+        rng = np.random.RandomState(0)
+        bc = BatchedCloth(L.default_params(), n, dtype=dt)
+        for _ in range(int(os.environ.get("PRE", "2"))):
+            bc.step_actions(torch.from_numpy(actions(rng, n)).to("cuda", dt))
+        torch.cuda.synchronize()
+        keep = [t.clone() for t in (bc.pos, bc.prev, bc.flags, bc.cost)]
+        a = torch.from_numpy(actions(rng, n)).to("cuda", dt)
+        def run(label, cost=None, sched=True):
+            bc.pos.copy_(keep[0]); bc.prev.copy_(keep[1]); bc.flags.copy_(keep[2]); bc.cost.copy_(keep[3] if cost is None else cost)
+            bc.schedule = sched
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); bc.step_actions(a); e1.record(); torch.cuda.synchronize()
+            busy = (bc.cost.double() * bc.sim_steps.double() / 1.9e6).cpu().numpy()
+            print("%-16s kernel %.1f ms | per-env busy max %.1f p99 %.1f mean(active) %.1f | sum/slots %.1f | active %d" % (
+                label, e0.elapsed_time(e1), busy.max(), np.percentile(busy, 99), busy[busy > 0].mean(), busy.sum() / 1184, (busy > 0).sum()))
+            return bc.cost.clone()
+        c1 = run("predicted")
+        c2 = run("exact cost", cost=c1)
+        run("exact cost again", cost=c2)
+        run("no scheduling", sched=False)
+        pred = (keep[3].double() * bc.sim_steps.double()).cpu().numpy(); act = (c1.double() * bc.sim_steps.double()).cpu().numpy()
+        m = act > 0
+        print("prediction error (active envs): corr %.3f, |pred/act-1| p50 %.2f p90 %.2f; envs with unknown cost %d" % (
+            np.corrcoef(pred[m], act[m])[0, 1], np.percentile(np.abs(pred[m] / act[m] - 1), 50), np.percentile(np.abs(pred[m] / act[m] - 1), 90),
+            int((keep[3][torch.from_numpy(m).cuda()] <= 0).sum().item())))
     elif what == "timeline":
         import ctypes as C
         dt = torch.float32
