@@ -11,6 +11,7 @@ import os
 CFG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cfg")
 
 
-def cfg_path(tier):
-    """Path of the tier-{1,2,3} configuration (values of the reference's cfg/t{tier}_rgbd.yaml, 1-D observation)."""
-    return os.path.join(CFG_DIR, "t%d_1d.yaml" % int(tier))
+def cfg_path(tier, obs="1d"):
+    """Path of the tier-{1,2,3} configuration (values of the reference's cfg/t{tier}_rgbd.yaml).
+    obs='1d': the 1-D observation; obs='rgbd': the reference's own obs_type 'blender' image observations."""
+    return os.path.join(CFG_DIR, "t%d_%s.yaml" % (int(tier), obs))

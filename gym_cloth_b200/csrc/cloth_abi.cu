@@ -92,6 +92,7 @@ const uint32_t *get_sweep_table(int W, int *levels, int *lw) {
     int broadcast_state_##SFX(int, int, const T *, const T *, T *, T *, cudaStream_t);                                                   \
     int gripper_adjust_##SFX(int, int, double, double, double, T *, T *, cudaStream_t);                                                  \
     int gripper_release_##SFX(int, int, T *, T *, cudaStream_t);                                                                         \
+    int render_##SFX(const ClothB200Params *, const ClothB200Scene *, const ClothB200SceneEnv *, int, const T *, int, uint8_t *, float *, unsigned *, cudaStream_t); \
     size_t step_smem_##SFX(const ClothB200Params *);
 DECL_TYPED(f32, float)
 DECL_TYPED(f64, double)
@@ -195,6 +196,51 @@ __global__ void __launch_bounds__(1024) fp32_fma_kernel(int iters, float *sink) 
     }
     const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456f) sink[0] = s;
+}
+
+// ---- what cloth_env.py does to the PNG Blender wrote (cloth_env.py:296-315) ----
+// cv2.bilateralFilter(img, 7, 50, 50) on a three-channel image whose channels are equal: radius 3, circular support,
+// BORDER_REFLECT_101, colour distance = sum of the three channel differences; then max(0, img - sub) and the noise
+__global__ void post_depth_kernel(int n, int H, int W, const uint8_t *__restrict__ gray, const float *__restrict__ sub,
+                                  const float *__restrict__ noise, uint8_t *__restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * H * W) return;
+    const int e = (int)(i / ((size_t)H * W));
+    const int r = (int)((i / W) % H), c = (int)(i % W);
+    const uint8_t *img = gray + (size_t)e * H * W;
+    const int v0 = img[r * W + c];
+    const float gc = -0.5f / (50.f * 50.f), gs = -0.5f / (50.f * 50.f);
+    float sum = 0.f, wsum = 0.f;
+    for (int di = -3; di <= 3; di++)
+        for (int dj = -3; dj <= 3; dj++) {
+            const int rr2 = di * di + dj * dj;
+            if (rr2 > 9) continue;
+            int y = r + di, x = c + dj;
+            y = y < 0 ? -y : (y >= H ? 2 * H - 2 - y : y);
+            x = x < 0 ? -x : (x >= W ? 2 * W - 2 - x : x);
+            const int v = img[y * W + x];
+            const int dc = 3 * abs(v - v0);
+            const float w = expf((float)rr2 * gs) * expf((float)(dc * dc) * gc);
+            sum += (float)v * w; wsum += w;
+        }
+    const int f = __float2int_rn(sum * (1.f / wsum));
+    const double g = sub ? (double)sub[e] : 50.0;
+    double d = (double)f - g;
+    const uint8_t v1 = (uint8_t)(d > 0.0 ? d : 0.0);                      // np.uint8(np.maximum(0, np.double(img) - gval))
+    for (int ch = 0; ch < 3; ch++) {
+        uint8_t o = v1;
+        if (noise) { double t = (double)v1 + (double)noise[3 * i + ch]; t = t < 0.0 ? 0.0 : (t > 255.0 ? 255.0 : t); o = (uint8_t)t; }
+        out[3 * i + ch] = o;
+    }
+}
+__global__ void post_rgb_kernel(int n, int H, int W, uint8_t *__restrict__ bgr, const uint8_t *__restrict__ lut, const float *__restrict__ noise) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * H * W * 3) return;
+    const int e = (int)(i / ((size_t)H * W * 3));
+    uint8_t v = bgr[i];
+    if (lut) v = lut[256 * e + v];                                         // cv2.LUT(image, table), cloth_env.py:1217-1228
+    if (noise) { double t = (double)v + (double)noise[i]; t = t < 0.0 ? 0.0 : (t > 255.0 ? 255.0 : t); v = (uint8_t)t; }
+    bgr[i] = v;
 }
 }  // namespace clothb200
 
@@ -339,6 +385,42 @@ int clothb200_gripper_adjust_f32(int np, int n, double x, double y, double z, fl
 int clothb200_gripper_adjust_f64(int np, int n, double x, double y, double z, double *pos, double *prev, void *st) { return gripper_adjust_f64(np, n, x, y, z, pos, prev, (cudaStream_t)st); }
 int clothb200_gripper_release_f32(int np, int n, float *pos, float *prev, void *st) { return gripper_release_f32(np, n, pos, prev, (cudaStream_t)st); }
 int clothb200_gripper_release_f64(int np, int n, double *pos, double *prev, void *st) { return gripper_release_f64(np, n, pos, prev, (cudaStream_t)st); }
+size_t clothb200_sizeof_scene(void) { return sizeof(ClothB200Scene); }
+int clothb200_scene_default(ClothB200Scene *s) {
+    if (!s) return CLOTHB200_ERR_ARG;
+    memset(s, 0, sizeof(*s));
+    s->height = 224; s->width = 224; s->samples = 2;
+    s->lens_mm = 40.f; s->sensor_mm = 36.f;
+    s->cam_pos[0] = 0.5f; s->cam_pos[1] = 0.5f; s->cam_pos[2] = 1.45f;
+    s->lamp_pos[0] = 4.07625f; s->lamp_pos[1] = 1.00545f; s->lamp_pos[2] = 5.90386f;
+    s->lamp_energy = 1.5f; s->diffuse_intensity = 0.8f; s->horizon = 0.051f;
+    s->bed_z = -0.05f; s->bed_x0 = 0.f; s->bed_x1 = 1.f; s->bed_y0 = 0.f; s->bed_y1 = 1.f;
+    s->floor_z = -0.25f; s->floor_x0 = -0.5f; s->floor_x1 = 1.5f; s->floor_y0 = -0.25f; s->floor_y1 = 1.25f;
+    s->front[0] = 0.070f; s->front[1] = 0.050f; s->front[2] = 0.600f;
+    s->back[0] = 0.070f; s->back[1] = 0.300f; s->back[2] = 0.900f;
+    s->bed[0] = 1.f; s->bed[1] = 1.f; s->bed[2] = 1.f;
+    return CLOTHB200_OK;
+}
+int clothb200_render_rgb_f32(const ClothB200Params *p, const ClothB200Scene *sc, const ClothB200SceneEnv *env, int n, const float *pos, uint8_t *out, void *st) { return render_f32(p, sc, env, n, pos, 0, out, nullptr, nullptr, (cudaStream_t)st); }
+int clothb200_render_rgb_f64(const ClothB200Params *p, const ClothB200Scene *sc, const ClothB200SceneEnv *env, int n, const double *pos, uint8_t *out, void *st) { return render_f64(p, sc, env, n, pos, 0, out, nullptr, nullptr, (cudaStream_t)st); }
+int clothb200_render_depth_f32(const ClothB200Params *p, const ClothB200Scene *sc, const ClothB200SceneEnv *env, int n, const float *pos, float *zbuf, uint32_t *mm, uint8_t *out, void *st) { return render_f32(p, sc, env, n, pos, 1, out, zbuf, mm, (cudaStream_t)st); }
+int clothb200_render_depth_f64(const ClothB200Params *p, const ClothB200Scene *sc, const ClothB200SceneEnv *env, int n, const double *pos, float *zbuf, uint32_t *mm, uint8_t *out, void *st) { return render_f64(p, sc, env, n, pos, 1, out, zbuf, mm, (cudaStream_t)st); }
+int clothb200_post_depth(int n, int H, int W, const uint8_t *gray, const float *sub, const float *noise, uint8_t *out, void *st) {
+    if (n < 0 || H < 2 || W < 2 || (n > 0 && (!gray || !out))) return CLOTHB200_ERR_ARG;
+    if (n == 0) return CLOTHB200_OK;
+    const size_t tot = (size_t)n * H * W;
+    post_depth_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)st>>>(n, H, W, gray, sub, noise, out);
+    g_launch_count++;
+    return check_cuda(cudaGetLastError(), "post_depth launch");
+}
+int clothb200_post_rgb(int n, int H, int W, uint8_t *bgr, const uint8_t *lut, const float *noise, void *st) {
+    if (n < 0 || H < 1 || W < 1 || (n > 0 && !bgr)) return CLOTHB200_ERR_ARG;
+    if (n == 0 || (!lut && !noise)) return CLOTHB200_OK;
+    const size_t tot = (size_t)n * H * W * 3;
+    post_rgb_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)st>>>(n, H, W, bgr, lut, noise);
+    g_launch_count++;
+    return check_cuda(cudaGetLastError(), "post_rgb launch");
+}
 int clothb200_measure_f32(const ClothB200Params *p, int n, const ClothB200Step *io, void *st) { return measure_f32(p, n, io, (cudaStream_t)st); }
 int clothb200_measure_f64(const ClothB200Params *p, int n, const ClothB200Step *io, void *st) { return measure_f64(p, n, io, (cudaStream_t)st); }
 

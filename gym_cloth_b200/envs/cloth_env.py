@@ -74,8 +74,13 @@ class BatchedClothEnv(object):
         cfg = self.cfg
         self.P = _l.params_from_cfg(cfg)
         env = cfg["env"]
-        if env["obs_type"] != "1d":
-            raise ValueError(env["obs_type"])            # only the 1-D observation is on the hot path
+        self.obs_type = env["obs_type"]
+        if self.obs_type not in ("1d", "blender"):
+            raise ValueError(self.obs_type)              # cloth_env.py:155-156
+        # image observations (cloth_env.py:107-117): the flags are the strings 'True' / 'False' in the cfg
+        self.use_depth = str(env.get("use_depth", "False")) == "True"
+        self.use_rgbd = str(env.get("use_rgbd", "False")) == "True"
+        self.add_dom_rand = str(env.get("use_dom_rand", "False")).lower() == "true"
         self.reward_type = env["reward_type"]
         assert "coverage" in self.reward_type             # cloth_env.py:130
         if self.reward_type != "coverage-delta":
@@ -97,6 +102,16 @@ class BatchedClothEnv(object):
                                   init_type="tier1" if self.init_type == "tier3" else self.init_type,
                                   noise=np.zeros(self.N) if self.init_type == "tier2" else None)
         self.device = self.cloth.device
+        self.renderer = None
+        if self.obs_type == "blender":
+            from ..render import ClothRenderer
+            self.renderer = ClothRenderer(self.P, self.n_env, device=self.device)
+            hd, wd = self.renderer.H, self.renderer.W
+            self.observation_space = _Box(np.zeros((hd, wd, 3)), np.ones((hd, wd, 3)), dtype=np.uint8)   # cloth_env.py:149-154
+            self._dr = {"gval_depth": np.full(self.n_env, 50.0, np.float32), "gval_rgb": np.ones(self.n_env),
+                        "c": np.ones((self.n_env, 3), np.float32), "n1": np.zeros((self.n_env, 3), np.float32),
+                        "camera_pos": np.zeros((self.n_env, 3), np.float32), "camera_deg": np.zeros((self.n_env, 3), np.float32)}
+            self._noise = None
         self.init_side = np.ones(self.n_env, bool)
         self.start_coverage = torch.zeros(self.n_env, dtype=torch.float64, device=self.device)
         self.start_variance_inv = torch.zeros(self.n_env, dtype=torch.float64, device=self.device)
@@ -187,15 +202,58 @@ class BatchedClothEnv(object):
         self.start_coverage[idx_t] = c.coverage[idx_t]
         self.start_variance_inv[idx_t] = c.variance_inv[idx_t]
         c.prev_coverage[idx_t] = c.coverage[idx_t]
-        if self.dom_rand_draws:
-            # cloth_env.py:786-789 consumes np_random draws for image noise the 1-D observation never uses;
-            # replayed so that later resets of the same stream see the reference's numbers (App. B-1: _wd=_hd=224)
-            for e in envs:
-                rs = self.rngs[e]
-                rs.uniform(low=40, high=50); rs.uniform(low=0.7, high=1.3)
-                lim = rs.uniform(low=-15.0, high=15.0)
-                rs.uniform(low=-lim, high=lim, size=(224, 224, 3))
-        return c.obs
+        if self.dom_rand_draws or self.renderer is not None:
+            self._draw_dom_rand(envs)
+        return c.obs if self.renderer is None else self.image_obs()
+
+    def _draw_dom_rand(self, envs):
+        """Per-episode domain randomisation values, drawn in the reference's order from the reference's generators
+        (cloth_env.py:786-794: the first four from the env's np_random, the rest from the global np.random).  The 1-D
+        observation never uses them but the draws are replayed so that later resets see the reference's numbers."""
+        keep = self.renderer is not None and self.add_dom_rand
+        if keep and self._noise is None:
+            self._noise = torch.zeros(self.n_env, self.renderer.H, self.renderer.W, 3, dtype=torch.float32, device=self.device)
+        for e in envs:
+            rs = self.rngs[e]
+            gval_depth = rs.uniform(low=40, high=50); gval_rgb = rs.uniform(low=0.7, high=1.3)
+            lim = rs.uniform(low=-15.0, high=15.0)
+            noise = rs.uniform(low=-lim, high=lim, size=(224, 224, 3))
+            if self.renderer is None:
+                continue
+            c = np.random.uniform(low=0.4, high=0.6, size=(3,)); n1 = np.random.uniform(low=-0.35, high=0.35, size=(3,))
+            cp = np.random.normal(0., scale=0.04, size=(3,)); cd = np.random.normal(0., scale=0.90, size=(3,))
+            np.random.uniform(low=0.0, high=0.0)          # specular_max
+            if keep:
+                d = self._dr
+                d["gval_depth"][e] = gval_depth; d["gval_rgb"][e] = gval_rgb
+                d["c"][e] = c; d["n1"][e] = n1; d["camera_pos"][e] = cp; d["camera_deg"][e] = cd
+                self._noise[e] = torch.from_numpy(noise.astype(np.float32)).to(self.device)
+        if self.renderer is None:
+            return
+        r = self.renderer
+        # tier2 cloths dropped from the other side show their other face (get_image_rep_279.py:236-238)
+        swap = ((self.init_type == "tier2") & ~self.init_side).astype(np.int32)
+        r.set_env_values(swap_sides=swap)
+        if keep:
+            from ..render import gamma_lut
+            d = self._dr
+            back = np.clip(np.array([0.070, 0.300, 0.900]) + d["n1"], 0.0, 1.0)     # get_image_rep_279.py:248-253
+            front = np.clip(np.array([0.070, 0.050, 0.600]) + d["n1"], 0.0, 1.0)
+            r.set_env_values(cam_pos_offset=d["camera_pos"], cam_deg=d["camera_deg"], front=front, back=back, bed=d["c"])
+            self._lut = torch.from_numpy(np.stack([gamma_lut(g) for g in d["gval_rgb"]])).to(self.device)
+            self._sub = torch.from_numpy(d["gval_depth"]).to(self.device)
+
+    def image_obs(self):
+        """The observation of obs_type 'blender' (cloth_env.py:201-209): uint8 [n_env, 224, 224, 3], BGR or depth,
+        or [.., 4] = BGR + depth when use_rgbd."""
+        r, pos = self.renderer, self.cloth.pos
+        dr = self.add_dom_rand
+        lut, sub, noise = (self._lut, self._sub, self._noise) if dr else (None, None, None)
+        if self.use_rgbd:
+            return r.rgbd(pos, lut=lut, sub=sub, noise_rgb=noise, noise_depth=noise)
+        if self.use_depth:
+            return r.depth(pos, sub=sub, noise=noise)
+        return r.rgb(pos, lut=lut, noise=noise)
 
     def _clip_space(self, x, y, dx, dy):   # _convert_action_to_clip_space, cloth_env.py:1207-1215
         return ((x - 0.5) * 2, (y - 0.5) * 2, dx, dy)
@@ -275,7 +333,7 @@ class BatchedClothEnv(object):
         c = self.cloth
         if isinstance(actions, torch.Tensor) and actions.is_cuda:
             c.step_actions(actions.to(self.torch_dtype).contiguous())
-            obs, rew, done = c.obs, c.reward, c.done
+            obs, rew, done = (c.obs if self.renderer is None else self.image_obs()), c.reward, c.done
             info = self._info(c.coverage, c.variance_inv, c.flags, c.num_steps, c.num_sim_steps)
             return obs, rew, done, info
         a = np.asarray(actions, np.float64).reshape(self.n_env, 4)
@@ -283,6 +341,13 @@ class BatchedClothEnv(object):
         c.step_host(a, out)
         info = self._info(out["coverage"], out["variance_inv"], out["flags"], None, None)
         info["sim_steps"] = out["sim_steps"]
+        if self.renderer is not None:
+            img = self.image_obs()
+            if getattr(self, "_host_img", None) is None or self._host_img.shape != img.shape:
+                self._host_img = torch.zeros(img.shape, dtype=torch.uint8).pin_memory()
+            self._host_img.copy_(img, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._host_img.numpy(), out["reward"], out["done"], info
         return out["obs"], out["reward"], out["done"], info
 
     def host_buffers(self):
@@ -457,7 +522,9 @@ class ClothEnv(object):
         return self._b.seed(seed)
 
     @property
-    def state(self):                       # cloth_env.py:188-200
+    def state(self):                       # cloth_env.py:188-209
+        if self._b.renderer is not None:
+            return self._b.image_obs()[0].cpu().numpy()
         return self.cloth.allpts_arr.reshape(-1)
 
     def _sync_counters(self):
@@ -503,6 +570,8 @@ class ClothEnv(object):
                     "actual_coverage": self._current_coverage, "start_coverage": self._start_coverage,
                     "variance_inv": float(info["variance_inv"][0]), "start_variance_inv": self._start_variance_inv,
                     "have_tear": self.have_tear, "out_of_bounds": bool(info["out_of_bounds"][0])}
+        if b.renderer is not None:
+            return np.array(obs[0]), float(rew[0]), bool(done[0]), out_info
         return np.array(obs[0], np.float64), float(rew[0]), bool(done[0]), out_info
 
     def _compute_coverage(self):

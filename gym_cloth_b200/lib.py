@@ -57,9 +57,30 @@ class Step(C.Structure):
     ]
 
 
+class Scene(C.Structure):
+    """ClothB200Scene: the Blender scene of gym_cloth/blender/get_image_rep_279.py."""
+    _f3 = C.c_float * 3
+    _fields_ = [
+        ("height", C.c_int32), ("width", C.c_int32), ("samples", C.c_int32), ("reserved", C.c_int32),
+        ("lens_mm", C.c_float), ("sensor_mm", C.c_float),
+        ("cam_pos", _f3), ("cam_deg", _f3), ("lamp_pos", _f3),
+        ("lamp_energy", C.c_float), ("diffuse_intensity", C.c_float), ("horizon", C.c_float),
+        ("bed_z", C.c_float), ("bed_x0", C.c_float), ("bed_x1", C.c_float), ("bed_y0", C.c_float), ("bed_y1", C.c_float),
+        ("floor_z", C.c_float), ("floor_x0", C.c_float), ("floor_x1", C.c_float), ("floor_y0", C.c_float), ("floor_y1", C.c_float),
+        ("front", _f3), ("back", _f3), ("bed", _f3),
+    ]
+
+
+class SceneEnv(C.Structure):
+    """ClothB200SceneEnv: optional per-environment scene values (device pointers)."""
+    _fields_ = [("cam_pos_offset", C.c_void_p), ("cam_deg", C.c_void_p), ("front", C.c_void_p), ("back", C.c_void_p),
+                ("bed", C.c_void_p), ("swap_sides", C.c_void_p)]
+
+
 # name -> (restype, argtypes); `None` suffix-expanded for _f32/_f64
 _vp, _i, _d, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
 _PP, _SP = C.POINTER(Params), C.POINTER(Step)
+_ScP, _SeP = C.POINTER(Scene), C.POINTER(SceneEnv)
 _PROTOS = {
     "clothb200_version": (_i, []),
     "clothb200_error_string": (C.c_char_p, [_i]),
@@ -76,6 +97,10 @@ _PROTOS = {
     "clothb200_bench_fp32_flops": (_i, [_i, C.POINTER(_d), _vp]),
     "clothb200_launch_count": (_i64, []),
     "clothb200_debug_set_profile": (_i, [_vp]),
+    "clothb200_sizeof_scene": (C.c_size_t, []),
+    "clothb200_scene_default": (_i, [_ScP]),
+    "clothb200_post_depth": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "clothb200_post_rgb": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 _TYPED = {
     "clothb200_init_grid": (_i, [_PP, _i, _vp, _i, _vp, _vp, _vp]),
@@ -89,6 +114,8 @@ _TYPED = {
     "clothb200_gripper_release": (_i, [_i, _i, _vp, _vp, _vp]),
     "clothb200_measure": (_i, [_PP, _i, _SP, _vp]),
     "clothb200_step_host": (_i, [_PP, _i, _i, _vp, _SP, _i] + [_vp] * 8),
+    "clothb200_render_rgb": (_i, [_PP, _ScP, _SeP, _i, _vp, _vp, _vp]),
+    "clothb200_render_depth": (_i, [_PP, _ScP, _SeP, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -119,6 +146,7 @@ def lib():
     assert L.clothb200_sizeof_params() == C.sizeof(Params), "Params layout mismatch"
     assert L.clothb200_sizeof_plan() == C.sizeof(Plan), "Plan layout mismatch"
     assert L.clothb200_sizeof_step() == C.sizeof(Step), "Step layout mismatch"
+    assert L.clothb200_sizeof_scene() == C.sizeof(Scene), "Scene layout mismatch"
     _lib = L
     return L
 
@@ -136,6 +164,12 @@ def default_params():
     P = Params()
     check(lib().clothb200_params_default(C.byref(P)), "params_default")
     return P
+
+
+def default_scene():
+    S = Scene()
+    check(lib().clothb200_scene_default(C.byref(S)), "scene_default")
+    return S
 
 
 def params_from_cfg(cfg):

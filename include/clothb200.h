@@ -199,6 +199,52 @@ int clothb200_step_host_f64(const ClothB200Params *params, int mode, int n_env, 
                             const ClothB200Step *io, int initialize, double *obs, double *reward, int32_t *done,
                             double *coverage, double *variance_inv, int32_t *flags, int32_t *sim_steps, void *stream);
 
+/* ---- image observations: the scene gym_cloth/blender/get_image_rep_279.py builds, rendered on
+ * the GPU instead of exporting an .obj and starting Blender per observation (cloth_env.py:212-330).  Blender is not
+ * available to pin pixel values; geometry (camera, planes, mesh, which side is visible) follows the script. ---- */
+typedef struct ClothB200Scene {
+    int32_t height, width;       /* 224 x 224 (cloth_env.py:150-151) */
+    int32_t samples;             /* colour image: samples x samples sub-pixel grid (depth images use the pixel centre) */
+    int32_t reserved;
+    float lens_mm, sensor_mm;    /* 40 / 36 (get_image_rep_279.py:267-277) */
+    float cam_pos[3];            /* 0.5, 0.5, 1.45 (:114-117) */
+    float cam_deg[3];            /* XYZ Euler degrees, 0 = straight down (:119-122) */
+    float lamp_pos[3];           /* the default scene's point lamp; NOSHADOW, CONSTANT falloff (:467-468) */
+    float lamp_energy;           /* 1.5 (:469) */
+    float diffuse_intensity;     /* 0.8, Blender's material default */
+    float horizon;               /* world colour behind everything, linear (0.051) */
+    float bed_z, bed_x0, bed_x1, bed_y0, bed_y1;            /* frame0.obj placed by set_bed_pose (:143-156): unit square, z = -0.05 */
+    float floor_z, floor_x0, floor_x1, floor_y0, floor_y1;  /* floor.obj, depth images only (:126-140, :455-462): z = -0.25 */
+    float front[3], back[3], bed[3];                        /* linear RGB (:249-253, :171) */
+} ClothB200Scene;
+/* optional per-environment values (domain randomisation, cloth_env.py:786-794), DEVICE pointers, NULL = scene value */
+typedef struct ClothB200SceneEnv {
+    const float *cam_pos_offset; /* [n_env][3] added to cam_pos */
+    const float *cam_deg;        /* [n_env][3] added to cam_deg */
+    const float *front, *back, *bed; /* [n_env][3] */
+    const int32_t *swap_sides;   /* [n_env] nonzero: colours of the two sides exchanged (tier2 && init_side == -1, :236-238) */
+} ClothB200SceneEnv;
+size_t clothb200_sizeof_scene(void);
+int clothb200_scene_default(ClothB200Scene *scene);
+/* colour image, uint8 BGR [n_env][height][width][3] (the channel order cv2.imread returns, cloth_env.py:292) */
+int clothb200_render_rgb_f32(const ClothB200Params *params, const ClothB200Scene *scene, const ClothB200SceneEnv *env, int n_env,
+                             const float *pos, uint8_t *out_bgr, void *stream);
+int clothb200_render_rgb_f64(const ClothB200Params *params, const ClothB200Scene *scene, const ClothB200SceneEnv *env, int n_env,
+                             const double *pos, uint8_t *out_bgr, void *stream);
+/* depth image as Blender writes it: camera-space Z normalised over the frame, display transform, uint8 [n_env][height][width].
+ * zbuf_scratch DEVICE float [n_env][height][width], minmax_scratch DEVICE uint32 [n_env][2]. */
+int clothb200_render_depth_f32(const ClothB200Params *params, const ClothB200Scene *scene, const ClothB200SceneEnv *env, int n_env,
+                               const float *pos, float *zbuf_scratch, uint32_t *minmax_scratch, uint8_t *out_gray, void *stream);
+int clothb200_render_depth_f64(const ClothB200Params *params, const ClothB200Scene *scene, const ClothB200SceneEnv *env, int n_env,
+                               const double *pos, float *zbuf_scratch, uint32_t *minmax_scratch, uint8_t *out_gray, void *stream);
+/* what cloth_env.py does to the loaded PNG (:296-315).  Depth: cv2.bilateralFilter(img, 7, 50, 50), subtract `sub`
+ * ([n_env] or NULL = 50), optional noise, written as three equal-source channels [n_env][h][w][3].  Colour: gamma
+ * lookup table ([n_env][256] uint8 as _adjust_gamma builds it, or NULL) and optional noise, in place.
+ * noise: DEVICE float [n_env][h][w][3] or NULL. */
+int clothb200_post_depth(int n_env, int height, int width, const uint8_t *gray, const float *sub, const float *noise,
+                         uint8_t *out_3ch, void *stream);
+int clothb200_post_rgb(int n_env, int height, int width, uint8_t *bgr, const uint8_t *lut, const float *noise, void *stream);
+
 /* ---- measurement helpers used by bench.py (microbenchmarks of this GPU's shared-memory and FP32 peaks) ---- */
 int clothb200_bench_smem_bandwidth(int iters, double *gb_per_s, void *stream);
 int clothb200_bench_fp32_flops(int iters, double *tflop_per_s, void *stream);
