@@ -196,6 +196,9 @@ class BatchedClothEnv(object):
             c.reset_grid("tier1", envs=envs)
         idx_t = torch.as_tensor(envs, device=self.device)
         c.num_steps[idx_t] = 0; c.num_sim_steps[idx_t] = 0
+        if getattr(self, "orig_pos", None) is None:
+            self.orig_pos = torch.zeros(self.n_env, self.N, 3, dtype=torch.float64, device=self.device)
+        self.orig_pos[idx_t] = c.pos[idx_t, :, :3].double()       # Point.orig_x/y/z (point.pyx: set once at construction)
         self.init_actions = {int(e): [] for e in envs}
         self._reset_actions(envs, sides)
         self._measure_subset(envs)
@@ -218,8 +221,7 @@ class BatchedClothEnv(object):
             gval_depth = rs.uniform(low=40, high=50); gval_rgb = rs.uniform(low=0.7, high=1.3)
             lim = rs.uniform(low=-15.0, high=15.0)
             noise = rs.uniform(low=-lim, high=lim, size=(224, 224, 3))
-            if self.renderer is None:
-                continue
+            # these come from the global generator in the reference, whatever the observation type (:790-794)
             c = np.random.uniform(low=0.4, high=0.6, size=(3,)); n1 = np.random.uniform(low=-0.35, high=0.35, size=(3,))
             cp = np.random.normal(0., scale=0.04, size=(3,)); cd = np.random.normal(0., scale=0.90, size=(3,))
             np.random.uniform(low=0.0, high=0.0)          # specular_max
@@ -547,7 +549,10 @@ class ClothEnv(object):
         else:
             b.reset()
         self.cloth._invalidate()
-        self.cloth._orig = self.cloth.allpts_arr if self.cloth._orig is None else self.cloth._orig
+        if self._start_state is None:
+            self.cloth._orig = b.orig_pos[0].cpu().numpy()
+        elif self.cloth._orig is None:
+            self.cloth._orig = self.cloth.allpts_arr
         self._sync_counters()
         self._start_coverage = float(b.start_coverage[0].item())
         self._start_variance_inv = float(b.start_variance_inv[0].item())

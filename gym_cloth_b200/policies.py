@@ -57,6 +57,34 @@ class OracleCornerPolicy(Policy):
         return (cx, cy, dx, dy) if self.cfg["env"]["clip_act_space"] else (x, y, dx, dy)
 
 
+class HighestPointPolicy(Policy):
+    """Pull one of the `top_k` highest points (chosen with the global np.random, as the reference does) 90 % of the
+    way to where that point sits on the flat grid (analytic.py:716-808)."""
+
+    def __init__(self):
+        self.top_k = 5
+
+    def _get_targ_xy(self, pt):                          # analytic.py:741-790
+        if self.cfg["init"]["type"] in ("tier1", "tier3"):
+            return pt.orig_x, pt.orig_y
+        if self.env.cloth.init_side:
+            return pt.orig_z, pt.orig_y
+        return 1.0 - pt.orig_z, pt.orig_y
+
+    def get_action(self, obs, t):
+        assert self.cfg["env"]["delta_actions"]
+        pts = self.env.cloth.pts
+        order = sorted(range(len(pts)), key=lambda i: pts[i].z, reverse=True)      # stable, like sorted(pts, key=z)
+        pt = pts[order[np.random.randint(self.top_k)]]
+        targx, targy = self._get_targ_xy(pt)
+        x, y = pt.x, pt.y
+        cx = (x - 0.5) * 2.0
+        cy = (y - 0.5) * 2.0
+        dx = (targx - x) * 0.90
+        dy = (targy - y) * 0.90
+        return (cx, cy, dx, dy) if self.cfg["env"]["clip_act_space"] else (x, y, dx, dy)
+
+
 class RandomPolicy(Policy):                             # analytic.py:811-822
     def get_action(self, obs, t):
         return self.env.get_random_action(atype="over_xy_plane")
@@ -79,3 +107,25 @@ def oracle_corner_actions(benv):
     tsel = targ[0][k]
     act = torch.cat([(sel - 0.5) * 2.0, (tsel - sel) * 0.90], dim=1)
     return act.to(c.dtype)
+
+
+def highest_point_actions(benv, top_k=5, generator=None):
+    """Batched HighestPointPolicy: [n_env, 4] actions (clip space).  One of each environment's `top_k` highest points
+    (ties in index order, like Python's stable sort) is chosen with `generator` (a torch.Generator on the env's device)."""
+    pos = benv.cloth.pos
+    n = benv.n_env
+    z = pos[:, :, 2].double()
+    order = torch.sort(z, dim=1, descending=True, stable=True).indices[:, :top_k]              # [n, k]
+    pick = torch.randint(0, top_k, (n,), device=pos.device, generator=generator)
+    ar = torch.arange(n, device=pos.device)
+    idx = order[ar, pick]
+    xy = pos[ar, idx, :2].double()
+    orig = benv.orig_pos[ar, idx]                                                               # [n, 3]
+    if benv.init_type == "tier2":
+        side = torch.as_tensor(benv.init_side, device=pos.device)
+        tx = torch.where(side, orig[:, 2], 1.0 - orig[:, 2])
+    else:
+        tx = orig[:, 0]
+    targ = torch.stack([tx, orig[:, 1]], dim=1)
+    act = torch.cat([(xy - 0.5) * 2.0, (targ - xy) * 0.90], dim=1)
+    return act.to(benv.torch_dtype)

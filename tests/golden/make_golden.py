@@ -253,18 +253,20 @@ def gen_env(out, tier, seed, n_actions, action_seed=None):
     np.savez_compressed(os.path.join(out, "env_t%d_s%d.npz" % (tier, seed)), **d)
 
 
-def gen_policy(out, tier=1, seed=1337, episodes=2):
+def gen_policy(out, tier=1, seed=1337, episodes=2, kind="oracle", max_t=None):
     """BASELINE config #1: the reference's own OracleCornerPolicy (examples/analytic.py:70-155) driving the reference
-    ClothEnv, tier 1.  Records every action the policy chose and what the env returned."""
+    ClothEnv, tier 1.  Records every action the policy chose and what the env returned.
+    kind='highest': HighestPointPolicy (analytic.py:716-808), which draws from the global np.random (seeded here)."""
     sys.path.insert(0, os.path.join(REFERENCE, "examples"))
     tmp = tempfile.mkdtemp(prefix="golden_pol_")
     env = _make_env(tier, seed, tmp)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         import analytic
-    policy = analytic.OracleCornerPolicy()
+    policy = analytic.OracleCornerPolicy() if kind == "oracle" else analytic.HighestPointPolicy()
     policy.set_env_cfg(env, env.cfg)
     d = {"tier": tier, "seed": seed}
+    np.random.seed(seed)
     ep_len = []
     k = 0
     for ep in range(episodes):
@@ -272,7 +274,7 @@ def gen_policy(out, tier=1, seed=1337, episodes=2):
         d["pos_reset_e%d" % ep] = _state(env.cloth)[0]
         d["start_coverage_e%d" % ep] = env._start_coverage
         done = False; t = 0
-        while not done:
+        while not done and (max_t is None or t < max_t):
             with contextlib.redirect_stdout(io.StringIO()):
                 a = policy.get_action(obs, t)
             obs, rew, done, info = env.step(a)
@@ -282,7 +284,7 @@ def gen_policy(out, tier=1, seed=1337, episodes=2):
             k += 1; t += 1
         ep_len.append(t)
     d["episode_lengths"] = np.array(ep_len)
-    np.savez_compressed(os.path.join(out, "policy_oracle_t%d_s%d.npz" % (tier, seed)), **d)
+    np.savez_compressed(os.path.join(out, "policy_%s_t%d_s%d.npz" % (kind, tier, seed)), **d)
 
 
 def gen_decode(out):
@@ -370,7 +372,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -384,11 +386,14 @@ def main():
                 ["env", "--tier", "1", "--seed", "1337", "--actions", "3"],
                 ["env", "--tier", "1", "--seed", "1338", "--actions", "3"],
                 ["env", "--tier", "2", "--seed", "1337", "--actions", "2"],
-                ["env", "--tier", "3", "--seed", "1337", "--actions", "2"], ["policy"]]
+                ["env", "--tier", "3", "--seed", "1337", "--actions", "2"], ["policy"],
+                ["policy_highest", "--tier", "3", "--seed", "1337"]]
         procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__)] + j + ["--out", a.out]) for j in jobs]
         rc = [p.wait() for p in procs]
         print("exit codes", rc)
         sys.exit(max(rc))
+    if a.what == "policy_highest":
+        return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="highest", max_t=3)
     {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy}.get(
         a.what, lambda out: gen_env(out, a.tier, a.seed, a.actions))(a.out)
 

@@ -68,3 +68,55 @@ def test_batched_oracle_policy_matches_single_env_policy_and_improves_coverage()
     after = info["actual_coverage"].mean().item()
     print("batched oracle policy: mean coverage %.3f -> %.3f after 3 actions (%d envs)" % (before, after, n))
     assert after > before + 0.05 and after > 0.9
+
+
+def test_highest_point_policy_matches_reference():
+    """HighestPointPolicy (analytic.py:716-808) on a tier-3 start: the reference draws the per-episode image
+    randomisation values and the policy's point choice from the GLOBAL np.random, so the whole episode only matches
+    if the facade consumes that stream in the reference's order, and `pt.orig_*` are the construction-time positions."""
+    from gym_cloth_b200 import cfg_path
+    from gym_cloth_b200.envs import ClothEnv
+    from gym_cloth_b200.policies import HighestPointPolicy
+    g = load_golden("policy_highest_t3_s1337.npz")
+    env = ClothEnv(cfg_path(3), dtype="f64")
+    env.seed(int(g["seed"]))
+    policy = HighestPointPolicy()
+    policy.set_env_cfg(env, env.cfg)
+    np.random.seed(int(g["seed"]))
+    obs = env.reset()
+    assert np.array_equal(obs.reshape(-1, 3), g["pos_reset_e0"])
+    for k in range(int(g["episode_lengths"][0])):
+        a = policy.get_action(obs, k)
+        assert np.array_equal(np.array(a, np.float64), g["action_%d" % k]), k
+        obs, rew, done, info = env.step(a)
+        rew_ref, done_ref, cov_ref, sim_ref = g["result_%d" % k]
+        assert np.array_equal(obs.reshape(-1, 3), g["pos_%d" % k])
+        assert abs(rew - rew_ref) < 1e-11 and done == bool(done_ref) and info["num_sim_steps"] == int(sim_ref)
+
+
+def test_batched_highest_point_policy():
+    from gym_cloth_b200 import cfg_path
+    from gym_cloth_b200.envs import BatchedClothEnv
+    from gym_cloth_b200.policies import highest_point_actions
+    n = 32
+    benv = BatchedClothEnv(cfg_path(3), n, dtype="f32", seed=77)
+    benv.reset()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    acts = highest_point_actions(benv, generator=gen)
+    assert acts.shape == (n, 4)
+    pos = benv.cloth.pos
+    z = pos[:, :, 2]
+    a = acts.double().cpu().numpy()
+    for e in range(n):
+        # the grabbed location is one of the five highest points, the pull goes 90 % of the way to its flat-grid place
+        xy = a[e, :2] / 2.0 + 0.5
+        top = torch.sort(z[e], descending=True, stable=True).indices[:5].cpu().numpy()
+        pts = pos[e, top, :2].double().cpu().numpy()
+        j = np.argmin(np.abs(pts - xy).sum(1))
+        assert np.abs(pts[j] - xy).max() < 1e-6
+        targ = benv.orig_pos[e, top[j], :2].cpu().numpy()
+        assert np.allclose(a[e, 2:], (targ - pts[j]) * 0.9, atol=1e-6)
+    cov0 = benv.start_coverage.mean().item()
+    for t in range(4):
+        obs, rew, done, info = benv.step(highest_point_actions(benv, generator=gen))
+    assert info["actual_coverage"].mean().item() > cov0
