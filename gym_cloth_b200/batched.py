@@ -48,11 +48,9 @@ class BatchedCloth(object):
         self.plans = torch.zeros(n, C.sizeof(_l.Plan), dtype=torch.uint8, device=dev)
         # longest-first scheduling state: measured cycles/substep per env + scratch for the on-device sort
         self.cost = torch.zeros(n, dtype=torch.float32, device=dev)
-        n2 = 1
-        while n2 < max(n, 1):
-            n2 *= 2
-        self.sched_scratch = torch.zeros(8 * n2 + 4 * n, dtype=torch.uint8, device=dev)
+        self.sched_scratch = torch.zeros(int(self.L.clothb200_sched_scratch_bytes(max(n, 1))), dtype=torch.uint8, device=dev)
         self.schedule = True
+        self.time_slice = True         # False: one CTA runs a whole action (ClothB200Step.sched_scratch_bytes = 0)
         self.iters_up_env = None
         self.env_order = None
         self.rest = None
@@ -93,6 +91,7 @@ class BatchedCloth(object):
         s.env_order = self.env_order.data_ptr() if self.env_order is not None else None
         s.cost = self.cost.data_ptr()
         s.sched_scratch = self.sched_scratch.data_ptr() if (self.schedule and self.env_order is None) else None
+        s.sched_scratch_bytes = self.sched_scratch.numel() if self.time_slice else 0
         return s
 
     # ------------------------------------------------------------------ construction (Cloth.__init__)

@@ -17,6 +17,11 @@
 namespace clothb200 {
 std::atomic<long long> g_launch_count{0};
 long long *g_prof_ptr = nullptr;
+int g_force_slots = 0, g_force_slice = 0;
+int slice_substeps() {
+    static int v = [] { const char *s = getenv("CLOTHB200_SLICE"); int x = s ? atoi(s) : 64; return x < 0 ? 0 : x; }();
+    return v;
+}
 int g_debug_flags = [] { const char *s = getenv("CLOTHB200_DEBUG"); return s ? atoi(s) : 0; }();
 static thread_local std::string g_cuda_err;
 void set_cuda_error(cudaError_t e, const char *where) {
@@ -265,6 +270,17 @@ const char *clothb200_last_cuda_error(void) { return g_cuda_err.c_str(); }
 size_t clothb200_sizeof_params(void) { return sizeof(ClothB200Params); }
 size_t clothb200_sizeof_plan(void) { return sizeof(ClothB200Plan); }
 size_t clothb200_sizeof_step(void) { return sizeof(ClothB200Step); }
+int clothb200_debug_set_slicing(int resident_ctas, int slice_substeps) {
+    g_force_slots = resident_ctas > 0 ? resident_ctas : 0;
+    g_force_slice = slice_substeps > 0 ? slice_substeps : 0;
+    return CLOTHB200_OK;
+}
+size_t clothb200_sched_scratch_bytes(int n_env) {
+    if (n_env < 1) return 0;
+    size_t np2 = 1; while (np2 < (size_t)n_env) np2 <<= 1;
+    // sort keys | launch order (padded to 8 bytes) | queue | progress, grip count, cycles | queue counters
+    return 8 * np2 + 8 * (((size_t)n_env + 1) / 2) + 8 * (size_t)n_env + 12 * (size_t)n_env + 16;
+}
 int64_t clothb200_launch_count(void) { return (int64_t)g_launch_count.load(); }
 int clothb200_debug_set_profile(void *dev_int64_nenv_x16) { g_prof_ptr = (long long *)dev_int64_nenv_x16; return CLOTHB200_OK; }
 

@@ -93,6 +93,14 @@ template <typename T> struct StepArgs {
     long long *prof;             // optional [n_env][16] cycle / event counters (debug)
     float *cost;                 // optional [n_env] in/out: SM cycles per substep of the env's last step
     int debug_flags;             // CLOTHB200_DEBUG env var: 1 = no warp-role rotation
+    // time-sliced mode (KMODE_STEP only, slice > 0): a persistent grid takes (item = position in the launch order)
+    // tickets from a queue, runs `slice` substeps of that cloth, stores it and re-queues it behind everything else
+    int slice, qcap;
+    unsigned long long *queue;   // [qcap] (ticket + 1) << 32 | estimated time left (2^14 cycles) << 16 | item
+    const unsigned long long *sorted_keys;   // plan_work_kernel's keys after the sort (substeps per item)
+    int *qctl;                   // [0] tickets taken, [1] tickets issued, [2] cloths finished
+    int *progress, *ngrab_s;     // [qcap] per item: substeps done, number of gripped points
+    float *cycles_s;             // [qcap] per item: SM cycles spent so far
 };
 
 enum { KMODE_STEP = 0, KMODE_UPDATE = 1, KMODE_GRAB = 2, KMODE_MEASURE = 3 };
@@ -138,6 +146,39 @@ __device__ __forceinline__ void bulk_commit_wait() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the stored bytes are complete in global memory (not just read out of shared memory) when this returns
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- work queue of the time-sliced step kernel (one thread per CTA calls these) ----
+// At most qcap items are alive, each at most once in the queue, so ticket t and ticket t + qcap can share a slot:
+// t + qcap can only be issued after the holder of t has read its slot (that cloth must be re-queued first).
+template <typename A_t> __device__ __forceinline__ int queue_pop(const A_t &A) {
+    const int t = atomicAdd(&A.qctl[0], 1);
+    volatile unsigned long long *slot = A.queue + (t % A.qcap);
+    volatile int *done = A.qctl + 2;
+    for (;;) {
+        const unsigned long long v = *slot;
+        if ((int)(v >> 32) == t + 1) { __threadfence(); return (int)(v & 0xffffull); }
+        if (*done >= A.qcap) return -1;
+        __nanosleep(200);
+    }
+}
+template <typename A_t> __device__ __forceinline__ void queue_push(const A_t &A, int item, int remaining) {
+    __threadfence();
+    const int t = atomicAdd(&A.qctl[1], 1);
+    const unsigned rem = (unsigned)(remaining > 65535 ? 65535 : remaining);
+    atomicExch(A.queue + (t % A.qcap), ((unsigned long long)(unsigned)(t + 1) << 32) | (rem << 16) | (unsigned)item);
+}
+// estimated time left of the cloth at the head of the queue (0 if nothing is waiting); a racy peek, only a heuristic
+template <typename A_t> __device__ __forceinline__ int queue_head_remaining(const A_t &A) {
+    const int h = *(volatile int *)&A.qctl[0];
+    const unsigned long long v = *(volatile unsigned long long *)(A.queue + (h % A.qcap));
+    return (int)(v >> 32) == h + 1 ? (int)((v >> 16) & 0xffffull) : 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // The per-CTA cloth.  NT threads; WC = compile-time grid width (0 = runtime).
@@ -428,6 +469,88 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     }
     // ordered replay of one bucket by one warp: from the first hit point on (nothing before it moved, so its
     // own evaluation equals the snapshot), in index order; contributions are summed in candidate order.
+    // A bucket of up to 32*K members replayed out of registers: lane l keeps members l, l+32, ... (bucket lists are
+    // in point-index order, so walking register set 0, then 1, ... visits the subjects in the reference's order and
+    // the per-set ballots add the contributions in candidate order).  Crumpled cloths pile 40-100 points into one
+    // cell; the shared-memory path below costs them 4x more per member.
+    template <int K> __device__ __forceinline__ void replay_bucket_regs(const int start, const int cnt, const int j0) {
+        int mine[K];
+        P4 Pm[K];
+        bool dirty[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int m = k * 32 + lane;
+            mine[k] = m < cnt ? lstB[start + m] : 0;
+            Pm[k] = pos[mine[k]];
+            dirty[k] = false;
+        }
+#pragma unroll
+        for (int kj = 0; kj < K; kj++) {
+            if (kj * 32 < cnt) {
+                // pinned members never move and are skipped as subjects (cloth.pyx:314-315)
+                unsigned todo = __ballot_sync(0xffffffffu, kj * 32 + lane < cnt && kj * 32 + lane >= j0 && Pm[kj].w == T(0));
+                while (todo) {
+                    const int jl = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const T px = __shfl_sync(0xffffffffu, Pm[kj].x, jl), py = __shfl_sync(0xffffffffu, Pm[kj].y, jl),
+                            pz = __shfl_sync(0xffffffffu, Pm[kj].z, jl);
+                    T t0 = T(0), t1 = T(0), t2 = T(0);
+                    int n = 0;
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        if (k * 32 < cnt) {
+                            const T d0 = px - Pm[k].x, d1 = py - Pm[k].y, d2 = pz - Pm[k].z;
+                            const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                            const bool hit = k * 32 + lane < cnt && !(k == kj && lane == jl) && within_thresh(qq);
+                            unsigned m = __ballot_sync(0xffffffffu, hit);
+                            if (m) {
+                                T c0 = T(0), c1 = T(0), c2 = T(0);
+                                if (hit) {
+                                    if (qq == T(0)) misc[3] = 1;
+                                    T factor;
+                                    if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                                    else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                                    c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
+                                }
+                                n += __popc(m);
+                                while (m) {
+                                    const int l = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    t0 += __shfl_sync(0xffffffffu, c0, l);
+                                    t1 += __shfl_sync(0xffffffffu, c1, l);
+                                    t2 += __shfl_sync(0xffffffffu, c2, l);
+                                }
+                            }
+                        }
+                    }
+                    if (n) {
+                        const T nf = (T)n;
+                        T cx, cy, cz;
+                        if (FAST) { const T inv = T(1) / (nf * P.sim_steps); cx = t0 * inv; cy = t1 * inv; cz = t2 * inv; }
+                        else { cx = t0 / nf / P.sim_steps; cy = t1 / nf / P.sim_steps; cz = t2 / nf / P.sim_steps; }
+                        if (lane == jl) { Pm[kj] = mk4(px + cx, py + cy, pz + cz, Pm[kj].w); dirty[kj] = true; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (k * 32 + lane < cnt) {
+                // plane collision (cloth.pyx:345-370) of my member, then one write-back
+                if (Pm[k].w == T(0) && !(Pm[k].z >= P.min_z)) {
+                    const P4 Q = prev[mine[k]];
+                    T t = (P.min_z - Q.z) * T(1.0);
+                    T tx = Q.x + t * T(-0.0), ty = Q.y + t * T(-0.0), tz = Q.z + t * T(-1.0);
+                    T gx = tx + P.surf_off * T(0.0), gy = ty + P.surf_off * T(0.0), gz = tz + P.surf_off * T(1.0);
+                    T ex = gx - Q.x, ey = gy - Q.y, ez = gz - Q.z;
+                    Pm[k] = mk4(Q.x + ex * P.fric1, Q.y + ey * P.fric1, Q.z + ez * P.fric1, Pm[k].w);
+                    dirty[k] = true;
+                }
+                if (dirty[k]) pos[mine[k]] = Pm[k];
+            }
+        }
+    }
+
     __device__ __forceinline__ void collide_replay() {
         for (int j = tid; j < P.ev_words; j += NT) ev[j] = 0u;   // pslot is dead from here on: its storage becomes the spring queue
         const int nwork = misc[1];
@@ -502,6 +625,10 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                     }
                     if (dirty) pos[mine] = Pm;
                 }
+            } else if (cnt <= 64) {
+                replay_bucket_regs<2>(start, cnt, j0);
+            } else if (cnt <= 128) {
+                replay_bucket_regs<4>(start, cnt, j0);
             } else {
                 for (int j = j0; j < cnt; j++) {
                     const int p = lstB[start + j];

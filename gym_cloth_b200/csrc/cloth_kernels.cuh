@@ -10,19 +10,41 @@ namespace clothb200 {
 
 extern std::atomic<long long> g_launch_count;   // defined in cloth_abi.cu
 extern int g_debug_flags;
+extern int g_force_slots, g_force_slice;         // tests: clothb200_debug_set_slicing
 extern long long *g_prof_ptr;                    // debug: per-env phase counters (clothb200_debug_set_profile)
 void set_cuda_error(cudaError_t e, const char *where);
 
 // ------------------------------------------------------------------------------------------------
 // The action kernel: one CTA = one cloth = one whole ClothEnv.step (or n bare updates).
 // ------------------------------------------------------------------------------------------------
+// f32, 128 threads: eight cloths per SM need <= 64 registers per thread (the shared-memory footprint allows exactly eight)
+template <typename T, int NT> struct MinBlocks { static constexpr int v = (sizeof(T) == 4 && NT == 128) ? 8 : 1; };
 template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED>
-__global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ DevParams<T> P, const __grid_constant__ StepArgs<T> A) {
+__global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(const __grid_constant__ DevParams<T> P, const __grid_constant__ StepArgs<T> A) {
     typedef ClothCTA<T, NT, WC, REST_TABLE, COLOURED> CTA;
     typedef typename CTA::P4 P4;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int env = A.env_order ? A.env_order[blockIdx.x] : (int)blockIdx.x;
     const int tid = threadIdx.x;
+    const bool sliced = A.slice > 0;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + CTA::smem_bytes(P.N, P.table_size, P.ev_words) - 16);
+    int *s_item = reinterpret_cast<int *>(bar + 1);     // the 8 bytes behind the mbarrier: item, progress << 16 | grip count
+    if (tid == 0) mbar_init(bar, 1);
+    uint32_t bar_phase = 0;
+  for (;;) {
+    int item = (int)blockIdx.x, i_begin = 0, ngrab_in = -1;
+    if (sliced) {
+        __syncthreads();
+        if (tid == 0) {
+            const int it = queue_pop(A);
+            s_item[0] = it;
+            if (it >= 0) { s_item[1] = (A.progress[it] << 16) | (A.ngrab_s[it] & 0xffff); fence_async_all(); }
+        }
+        __syncthreads();
+        item = s_item[0];
+        if (item < 0) return;
+        i_begin = s_item[1] >> 16; ngrab_in = s_item[1] & 0xffff;
+    }
+    const int env = A.env_order ? A.env_order[item] : item;
     const T *rest_env = REST_TABLE ? A.rest + (long long)env * A.rest_env_stride : nullptr;
     CTA c(P, smem, rest_env);
     c.prof_on = A.prof != nullptr;
@@ -30,12 +52,10 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     if (A.prof && threadIdx.x == 0) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0)); }
     if (A.debug_flags & 1) c.rot = 0;
     const int N = c.N;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + CTA::smem_bytes(N, P.table_size, P.ev_words) - 16);
     const uint32_t bytes = (uint32_t)(sizeof(P4) * (size_t)N);
     T *gpos = A.pos + (size_t)env * N * 4, *gprev = A.prev + (size_t)env * N * 4;
 
     // ---- stage the cloth into shared memory: two TMA bulk copies completing on one mbarrier ----
-    if (tid == 0) mbar_init(bar, 1);
     c.sync();
     if (tid == 0) {
         mbar_expect_tx(bar, 2 * bytes);
@@ -50,7 +70,8 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         c.kc[tid] = make_float2(r * 1.1f, ct * ct);
     }
     int flags_in = A.flags ? A.flags[env] : 0;
-    mbar_wait(bar, 0);
+    mbar_wait(bar, bar_phase);
+    bar_phase ^= 1u;
     c.sync();
     if (tid == 0) c.misc[2] = (flags_in & CLOTHB200_FLAG_TEAR) ? 1 : 0;
     if (tid == 0 && (flags_in & CLOTHB200_FLAG_BADSTATE)) c.misc[3] = 1;
@@ -63,15 +84,16 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
     const bool stepping = A.mode == KMODE_STEP;
     if (stepping) {
         const ClothB200Plan plan = A.plans[env];
-        ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
-        if (P.force_grab) {
+        if (i_begin > 0) ngrab = ngrab_in;            // resumed slice: the grip is part of the stored state
+        else ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
+        if (P.force_grab && i_begin == 0) {
             // cloth_env.py:434-444: `while len(grabbed_pts) == 0: grip_radius += 0.02; grab_top(...)` (radius restored afterwards).
             // A cloth with no point under z = height + 2*thickness can never be gripped; the reference would spin forever,
             // we stop once the cylinder covers any reachable (x, y) and report NOGRAB.
             double rad = P.grip_radius;
             for (int tries = 0; ngrab == 0 && tries < 4096; tries++) { rad += 0.02; ngrab = c.grab_top(plan.gx, plan.gy, rad); }
         }
-        if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+        if (A.grab_mask && i_begin == 0) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
         // _pull thresholds (cloth_env.py:352-367, 472-475): `i < t` for integer i <=> i < ceil(t)
         const double iu = A.iters_up_env ? A.iters_up_env[env] : P.iu;
         const double t1 = iu + P.iur, t2 = t1 + (double)plan.iters_pull, t3 = t2 + P.igr, t4 = t3 + P.ir;
@@ -84,21 +106,61 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         ngrab = c.grab_top(A.grab_xy[2 * env], A.grab_xy[2 * env + 1], A.grab_radius);
         if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
     }
-    bool released = false;
+    bool released = stepping && i_begin > e3;
+    int i_end = sliced ? min(iterations, i_begin + A.slice) : iterations;
     const long long t_loop0 = clock64();
-    for (int i = 0; i < iterations; i++) {
-        if (stepping) {
-            if (i < e0) { c.gripper_adjust(T(0.0), T(0.0), T(0.0025)); c.sync(); }
-            else if (i < e1) { }
-            else if (i < e2) { c.gripper_adjust(dxr, dyr, T(0.0)); c.sync(); }
-            else if (i < e3) { }
-            else if (!released) { c.gripper_release(); released = true; c.sync(); }
+    int i = i_begin;
+    bool broke = false, parked = false;
+    for (;;) {
+        for (; i < i_end; i++) {
+            if (stepping) {
+                if (i < e0) { c.gripper_adjust(T(0.0), T(0.0), T(0.0025)); c.sync(); }
+                else if (i < e1) { }
+                else if (i < e2) { c.gripper_adjust(dxr, dyr, T(0.0)); c.sync(); }
+                else if (i < e3) { }
+                else if (!released) { c.gripper_release(); released = true; c.sync(); }
+            }
+            c.update();
+            if (stepping && c.misc[2]) { broke = true; i++; break; }   // tear: cloth_env.py:511-514 (gripper is not released)
         }
-        c.update();
-        nupd++;
-        if (stepping && c.misc[2]) break;   // tear: cloth_env.py:511-514 (gripper is not released)
+        if (!sliced || broke || i >= iterations) break;
+        // ---- end of a slice: longest-remaining-first.  Keep the cloth unless a waiting one has more substeps left
+        // (then the launch ends at max(longest action, total work / slots) instead of with the last whole action) ----
+        if (tid == 0) {
+            // time left = substeps left x this action's measured cycles per substep (within an action that rate is
+            // steady, unlike from one action to the next), in units of 2^14 cycles
+            const float spent = (float)(clock64() - t_loop0) + (i_begin > 0 ? A.cycles_s[item] : 0.f);
+            const float left = (float)(iterations - i) * (spent / (float)i) * (1.0f / 16384.0f);
+            s_item[0] = (left < 65535.f ? (int)left : 65535);
+            s_item[1] = queue_head_remaining(A) > s_item[0] ? 1 : 0;
+        }
+        c.sync();
+        const bool yield = s_item[1] != 0;
+        const int left_units = s_item[0];
+        c.sync();
+        if (!yield) { i_end = min(iterations, i + A.slice); continue; }
+        const int bad_now = c.misc[3];
+        fence_async_smem();
+        c.sync();
+        if (tid == 0) {
+            bulk_s2g(gpos, c.pos, bytes);
+            bulk_s2g(gprev, c.prev, bytes);
+            A.progress[item] = i; A.ngrab_s[item] = ngrab;
+            A.cycles_s[item] = (float)(clock64() - t_loop0) + (i_begin > 0 ? A.cycles_s[item] : 0.f);
+            if (bad_now && A.flags) A.flags[env] = flags_in | CLOTHB200_FLAG_BADSTATE;
+            if (A.prof) for (int k = 0; k < 14; k++) A.prof[(size_t)env * 16 + k] += c.pacc[k];
+            bulk_commit_wait_all();
+            fence_async_all();
+            queue_push(A, item, left_units);
+        }
+        parked = true;
+        break;
     }
+    if (parked) continue;
+    nupd = i;
     const long long t_loop1 = clock64();
+    float cycles_total = (float)(t_loop1 - t_loop0);
+    if (sliced && i_begin > 0) cycles_total += A.cycles_s[item];
 
     // ---- reward terms ----
     const bool want_measure = (A.coverage || A.variance_inv || A.reward) && A.mode != KMODE_GRAB;
@@ -126,7 +188,7 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         T *o = A.obs + (size_t)env * 3 * N;
         for (int i = tid; i < 3 * N; i += NT) { const int p = i / 3; o[i] = flat[p * 4 + (i - p * 3)]; }
     }
-    if (tid == 0 && A.cost && stepping && nupd > 0) A.cost[env] = (float)(t_loop1 - t_loop0) / (float)nupd;
+    if (tid == 0 && A.cost && stepping && nupd > 0) A.cost[env] = cycles_total / (float)nupd;
     if (tid == 0) {
         int f = (tear ? CLOTHB200_FLAG_TEAR : 0) | (oob ? CLOTHB200_FLAG_OOB : 0) | (bad ? CLOTHB200_FLAG_BADSTATE : 0);
         if (A.mode == KMODE_STEP && ngrab == 0) f |= CLOTHB200_FLAG_NOGRAB;
@@ -158,17 +220,39 @@ __global__ void __launch_bounds__(NT) cloth_step_kernel(const __grid_constant__ 
         unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
         unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         if (A.debug_flags & 2) { c.pacc[14] = (long long)gt0; c.pacc[15] = (long long)gt1; c.pacc[11] = (long long)smid * 1000000 + c.pacc[11] % 1000000; }
-        c.pacc[10] = nupd;
-        for (int i = 0; i < 16; i++) A.prof[(size_t)env * 16 + i] = c.pacc[i];
+        if (sliced) {
+            for (int k = 0; k < 16; k++) if (k != 10) A.prof[(size_t)env * 16 + k] += c.pacc[k];
+            A.prof[(size_t)env * 16 + 10] = nupd;
+        } else {
+            c.pacc[10] = nupd;
+            for (int k = 0; k < 16; k++) A.prof[(size_t)env * 16 + k] = c.pacc[k];
+        }
     }
+    if (!sliced) return;
+    if (tid == 0) { __threadfence(); atomicAdd(&A.qctl[2], 1); }
+  }
+}
+
+// queue of the time-sliced mode: every item once, in launch order, with the substeps its plan will run
+static __global__ void queue_init_kernel(int n, const unsigned long long *keys, unsigned long long *queue, int *qctl, int *progress,
+                                         int *ngrab_s, float *cycles_s) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        // plan_work_kernel's key, after the sort: planned substeps; time left at a typical 1.2e5 cycles per substep,
+        // in the queue's units of 2^14 cycles
+        const float work = __uint_as_float(~(unsigned)(keys[j] >> 32));
+        const unsigned rem = (unsigned)fminf(fmaxf(work * (1.2e5f / 16384.0f), 0.f), 65535.f);
+        queue[j] = ((unsigned long long)(unsigned)(j + 1) << 32) | (rem << 16) | (unsigned)j;
+        progress[j] = 0; ngrab_s[j] = -1; cycles_s[j] = 0.f;
+    }
+    if (j == 0) { qctl[0] = 0; qctl[1] = n; qctl[2] = 0; qctl[3] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // longest-first scheduling: work estimate per environment, then a single-CTA bitonic sort of (work, env)
 // ------------------------------------------------------------------------------------------------
-// One warp per environment.  work = number of substeps the plan will run (0 if the grip catches nothing)
-// x the environment's last measured cycles per substep.  This only orders the launch: it is a heuristic
-// (the z-band test is simplified), results never depend on it.
+// One warp per environment.  work = number of substeps the plan will run (0 if the grip catches nothing).
+// This only orders the launch: it is a heuristic (the z-band test is simplified), results never depend on it.
 template <typename T>
 __global__ void plan_work_kernel(int n_env, int n_pow2, int N, const T *__restrict__ pos, const T *__restrict__ prev,
                                  const ClothB200Plan *__restrict__ plans, const float *__restrict__ cost, double grip_radius,
@@ -190,9 +274,11 @@ __global__ void plan_work_kernel(int n_env, int n_pow2, int N, const T *__restri
     if (lane == 0) {
         const double i0 = iters_up_env ? iters_up_env[env] : iu;
         const float iters = any ? (float)(i0 + iur + (double)pl.iters_pull + igr + ir) : 0.f;
-        float c = cost ? cost[env] : 0.f;
-        if (!(c > 0.f)) c = 1.0e5f;
-        const float work = iters * c;
+        // Measured (scripts/quick_bench.py sched, scripts/cost_model.py): an environment's cycles per substep in its
+        // last step says almost nothing about the coming one (correlation 0.08-0.25) and ordering by it is no better
+        // than not ordering, while the planned substep count alone orders as well as the exact cost would.
+        (void)cost;
+        const float work = iters;
         // descending by work: invert the (non-negative) float bits; ties by env id
         keys[env] = ((unsigned long long)(~__float_as_uint(work)) << 32) | (unsigned)env;
     }
@@ -355,13 +441,38 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
         if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(smem)"); return CLOTHB200_ERR_UNSUPPORTED; }
         configured = smem;
     }
-    kern<<<A.n_env, NT, smem, st>>>(P, A);
+    if (A.slice > 0) {
+        // time-sliced mode: a persistent grid, one CTA per resident slot; pointless when every cloth has its own slot
+        static int slots = 0;
+        if (!slots) {
+            int occ = 0, dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) occ = 1;
+            slots = occ * sms;
+        }
+        const int use_slots = g_force_slots > 0 ? g_force_slots : slots;
+        if (A.n_env > use_slots) {
+            queue_init_kernel<<<(A.n_env + 255) / 256, 256, 0, st>>>(A.n_env, A.sorted_keys, A.queue, A.qctl, A.progress, A.ngrab_s, A.cycles_s);
+            StepArgs<T> B = A;
+            if (g_force_slice > 0) B.slice = g_force_slice;
+            kern<<<use_slots, NT, smem, st>>>(P, B);
+            g_launch_count += 2;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { set_cuda_error(e, "cloth_step_kernel (sliced) launch"); return CLOTHB200_ERR_CUDA; }
+            return CLOTHB200_OK;
+        }
+    }
+    StepArgs<T> B = A;
+    B.slice = 0;
+    kern<<<A.n_env, NT, smem, st>>>(P, B);
     g_launch_count++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_cuda_error(e, "cloth_step_kernel launch"); return CLOTHB200_ERR_CUDA; }
     return CLOTHB200_OK;
 }
 
+int slice_substeps();           // cloth_abi.cu: CLOTHB200_SLICE env var; default 128, 0 = whole actions
 int threads_per_cloth(int W);   // cloth_abi.cu: CLOTHB200_NT env var; default 128 (512 for 64x64)
 
 template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {

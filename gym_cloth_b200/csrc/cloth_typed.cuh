@@ -58,6 +58,18 @@ int step_plans_t(const ClothB200Params *hp, int mode, int n_env, const ClothB200
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_cuda_error(e, "schedule kernels"); return CLOTHB200_ERR_CUDA; }
         A.env_order = order;
+        // time slicing (see StepArgs): needs the larger scratch; a debug timeline wants one CTA per cloth
+        const size_t need = clothb200_sched_scratch_bytes(n_env);
+        const int slice = slice_substeps();
+        if (slice > 0 && io->sched_scratch_bytes >= (int64_t)need && !(g_debug_flags & 2)) {
+            unsigned char *base = (unsigned char *)io->sched_scratch + (size_t)8 * n_pow2 + (size_t)8 * ((n_env + 1) / 2);
+            A.queue = (unsigned long long *)base;
+            A.progress = (int *)(base + (size_t)8 * n_env);
+            A.ngrab_s = A.progress + n_env;
+            A.cycles_s = (float *)(A.ngrab_s + n_env);
+            A.qctl = (int *)(A.cycles_s + n_env);
+            A.slice = slice; A.qcap = n_env; A.sorted_keys = keys;
+        }
     }
     return launch_step<T>(*hp, A, st, mode);
 }

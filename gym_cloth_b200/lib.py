@@ -53,7 +53,7 @@ class Step(C.Structure):
         ("prev_coverage", C.c_void_p), ("num_steps", C.c_void_p), ("num_sim_steps", C.c_void_p),
         ("reward", C.c_void_p), ("done", C.c_void_p),
         ("iters_up_env", C.c_void_p), ("env_order", C.c_void_p),
-        ("cost", C.c_void_p), ("sched_scratch", C.c_void_p),
+        ("cost", C.c_void_p), ("sched_scratch", C.c_void_p), ("sched_scratch_bytes", C.c_int64),
     ]
 
 
@@ -97,6 +97,8 @@ _PROTOS = {
     "clothb200_bench_fp32_flops": (_i, [_i, C.POINTER(_d), _vp]),
     "clothb200_launch_count": (_i64, []),
     "clothb200_debug_set_profile": (_i, [_vp]),
+    "clothb200_sched_scratch_bytes": (C.c_size_t, [_i]),
+    "clothb200_debug_set_slicing": (_i, [_i, _i]),
     "clothb200_sizeof_scene": (C.c_size_t, []),
     "clothb200_scene_default": (_i, [_ScP]),
     "clothb200_post_depth": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

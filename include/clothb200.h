@@ -108,11 +108,17 @@ typedef struct ClothB200Step {
     const double *iters_up_env;/* [n_env] optional per-env override of iters_up (tier-3 reset, cloth_env.py:960) */
     const int32_t *env_order;  /* [n_env] optional: explicit order in which CTAs pick environments; also selects a subset
                                   (n_env entries of a larger batch).  Overrides the built-in scheduling. */
-    float *cost;               /* [n_env] optional in/out: measured SM cycles per substep of each environment's last step
-                                  (0 = unknown); feeds the longest-first schedule */
-    void *sched_scratch;       /* optional DEVICE scratch, >= 8*pow2ceil(n_env) + 4*n_env bytes.  When given (and env_order
-                                  is NULL) step_plans/step_actions/step_host schedule environments longest-first:
-                                  work = substeps of the plan (0 if the grip catches nothing) x cost */
+    float *cost;               /* [n_env] optional out: measured SM cycles per substep of each environment's last step
+                                  (diagnostics; it does not predict the next step and is not used for scheduling) */
+    void *sched_scratch;       /* optional DEVICE scratch.  When given (and env_order is NULL) step_plans / step_actions /
+                                  step_host order environments by the substeps their plan will run (0 if the grip catches
+                                  nothing), longest first; needs >= 8*pow2ceil(n_env) + 4*n_env bytes. */
+    int64_t sched_scratch_bytes; /* size of sched_scratch.  With >= clothb200_sched_scratch_bytes(n_env) bytes and more
+                                  environments than resident CTAs (at most 65536), the step runs time-sliced: a
+                                  persistent grid runs CLOTHB200_SLICE (default 64) substeps of a cloth at a time and
+                                  swaps it for a waiting cloth that has more substeps left (longest remaining first), so
+                                  that a launch ends at max(longest action, total work / resident CTAs) rather than
+                                  with the last whole action.  Results do not depend on it. */
 } ClothB200Step;
 
 /* ---- library / device ---- */
@@ -250,6 +256,10 @@ int clothb200_bench_smem_bandwidth(int iters, double *gb_per_s, void *stream);
 int clothb200_bench_fp32_flops(int iters, double *tflop_per_s, void *stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t clothb200_launch_count(void);
+/* bytes of ClothB200Step.sched_scratch that enable the time-sliced step for n_env environments */
+size_t clothb200_sched_scratch_bytes(int n_env);
+/* tests: pretend the GPU holds `resident_ctas` cloths at once and slice every `slice_substeps` substeps (0, 0 = automatic) */
+int clothb200_debug_set_slicing(int resident_ctas, int slice_substeps);
 /* debug: DEVICE int64 [n_env][16]; when set, the step kernel records per-phase SM cycles of thread 0 and event counts
  * (0..9 phases of Cloth.update, 10 substeps, 11 replayed buckets, 12 limit-queue pops, 13 springs shortened). NULL = off. */
 int clothb200_debug_set_profile(void *dev_int64_nenv_x16);

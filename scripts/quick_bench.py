@@ -90,11 +90,12 @@ if __name__ == "__main__":
         for i, nm in enumerate(names):
             print("    %-18s %6.1f %%  %9.0f cyc/substep" % (nm, 100 * p[heavy, i].sum() / toth, p[heavy, i].sum() / nsh))
         idx = np.argsort(-np.where(act, p[:, :10].sum(1) / np.maximum(p[:, 10], 1), 0))
-        print("  env  substeps  cyc/substep  pops/sub  moved/sub  limit_replay cyc/pop  buckets/sub  coll_replay cyc/bucket")
+        print("  env  substeps  cyc/substep  pops/sub  moved/sub  limit_replay cyc/pop  buckets/sub  coll_replay cyc/bucket | small members/sub, big members/sub, big buckets/sub | phase cycles/sub: coll_replay limit_snap limit_replay")
         for e in list(idx[:8]) + list(idx[200:204]) + list(idx[600:604]):
             ns = p[e, 10]
             print("  %4d %8d %11.0f %9.1f %9.1f %12.0f %12.1f %12.0f" % (e, ns, p[e, :10].sum() / ns, p[e, 12] / ns, p[e, 13] / ns,
-                  p[e, 9] / max(p[e, 12], 1), p[e, 11] / ns, p[e, 7] / max(p[e, 11], 1)))
+                  p[e, 9] / max(p[e, 12], 1), p[e, 11] / ns, p[e, 7] / max(p[e, 11], 1)),
+                  "| %6.1f %6.1f %5.2f | %7.0f %7.0f %7.0f" % (p[e, 14] / ns, p[e, 15] / ns, p[e, 5] / ns, p[e, 7] / ns, p[e, 8] / ns, p[e, 9] / ns))
     elif what == "sched":
         # how much of the launch time is mis-prediction? run the same action from the same state three ways:
         # predicted costs (what a user gets), exact costs (from the first run), no scheduling
@@ -119,6 +120,10 @@ if __name__ == "__main__":
         c2 = run("exact cost", cost=c1)
         run("exact cost again", cost=c2)
         run("no scheduling", sched=False)
+        steps = bc.sim_steps.float()
+        run("key = substeps", cost=torch.full_like(c1, 1.0e5))
+        run("key = substeps^2", cost=steps.clamp(min=1.0) * 60.0)
+        run("key = substeps^3", cost=steps.clamp(min=1.0) ** 2 * 0.03)
         pred = (keep[3].double() * bc.sim_steps.double()).cpu().numpy(); act = (c1.double() * bc.sim_steps.double()).cpu().numpy()
         m = act > 0
         print("prediction error (active envs): corr %.3f, |pred/act-1| p50 %.2f p90 %.2f; envs with unknown cost %d" % (
