@@ -3,8 +3,9 @@
 
     python -m gym_cloth_b200.build [--force] [--verbose]
 
-Three translation units: cloth_f32.cu (production), cloth_f64.cu (parity build, -fmad=false so
-that every operator is one rounded IEEE operation) and cloth_abi.cu (extern "C" surface).
+Translation units, compiled in parallel: cloth_f32.cu (production entry points + renderer), cloth_f64.cu (parity
+build, -fmad=false so that every operator is one rounded IEEE operation), cloth_abi.cu (extern "C" surface) and
+cloth_inst.cu six times (the step kernel per scalar type and compile-time grid width).
 """
 import os
 import subprocess
@@ -19,7 +20,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # f32 (production): flush-to-zero and approximate div/sqrt - the parity contract of this build is a tolerance, and
 # IEEE fix-up sequences around every rsqrt/division are pure latency on the serial replay paths.
 # f64 (parity): no FMA contraction, IEEE everything.
-UNITS = [("cloth_f32.cu", ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]), ("cloth_f64.cu", ["-fmad=false"]), ("cloth_abi.cu", [])]
+F32 = ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]
+F64 = ["-fmad=false"]
+# (source, object name, flags); cloth_inst.cu holds the step kernel for one (scalar type, grid width) pair
+UNITS = [("cloth_f32.cu", "cloth_f32.o", F32), ("cloth_f64.cu", "cloth_f64.o", F64), ("cloth_abi.cu", "cloth_abi.o", [])]
+for _t, _sfx, _fl in (("float", "f32", F32), ("double", "f64", F64)):
+    for _w in (25, 0, 64):
+        UNITS.append(("cloth_inst.cu", "cloth_inst_%s_w%d.o" % (_sfx, _w), _fl + ["-DCLOTH_T=%s" % _t, "-DCLOTH_INSTANTIATE_WC=%d" % _w]))
 
 
 def _newest_src():
@@ -41,8 +48,8 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     procs = []
     objs = []
-    for src, extra in UNITS:
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    for src, oname, extra in UNITS:
+        obj = os.path.join(OBJ, oname)
         objs.append(obj)
         cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

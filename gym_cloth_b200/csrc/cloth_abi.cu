@@ -31,7 +31,7 @@ int threads_per_cloth(int W) {
     static int nt = [] {
         const char *s = getenv("CLOTHB200_NT");
         int v = s ? atoi(s) : 0;
-        return (v == 32 || v == 64 || v == 128 || v == 256 || v == 512) ? v : 0;
+        return (v == 128 || v == 256 || v == 512) ? v : 0;
     }();
     if (nt) return nt;
     return W >= 64 ? 512 : 128;

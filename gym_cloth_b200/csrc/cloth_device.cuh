@@ -96,7 +96,7 @@ template <typename T> struct StepArgs {
     // time-sliced mode (KMODE_STEP only, slice > 0): a persistent grid takes (item = position in the launch order)
     // tickets from a queue, runs `slice` substeps of that cloth, stores it and re-queues it behind everything else
     int slice, qcap;
-    unsigned long long *queue;   // [qcap] (ticket + 1) << 32 | estimated time left (2^14 cycles) << 16 | item
+    unsigned long long *queue;   // [qcap] (ticket + 1) << 32 | substeps left << 16 | item
     const unsigned long long *sorted_keys;   // plan_work_kernel's keys after the sort (substeps per item)
     int *qctl;                   // [0] tickets taken, [1] tickets issued, [2] cloths finished
     int *progress, *ngrab_s;     // [qcap] per item: substeps done, number of gripped points
@@ -173,7 +173,7 @@ template <typename A_t> __device__ __forceinline__ void queue_push(const A_t &A,
     const unsigned rem = (unsigned)(remaining > 65535 ? 65535 : remaining);
     atomicExch(A.queue + (t % A.qcap), ((unsigned long long)(unsigned)(t + 1) << 32) | (rem << 16) | (unsigned)item);
 }
-// estimated time left of the cloth at the head of the queue (0 if nothing is waiting); a racy peek, only a heuristic
+// substeps left of the cloth at the head of the queue (0 if nothing is waiting); a racy peek, only a heuristic
 template <typename A_t> __device__ __forceinline__ int queue_head_remaining(const A_t &A) {
     const int h = *(volatile int *)&A.qctl[0];
     const unsigned long long v = *(volatile unsigned long long *)(A.queue + (h % A.qcap));

@@ -126,14 +126,9 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
         if (!sliced || broke || i >= iterations) break;
         // ---- end of a slice: longest-remaining-first.  Keep the cloth unless a waiting one has more substeps left
         // (then the launch ends at max(longest action, total work / slots) instead of with the last whole action) ----
-        if (tid == 0) {
-            // time left = substeps left x this action's measured cycles per substep (within an action that rate is
-            // steady, unlike from one action to the next), in units of 2^14 cycles
-            const float spent = (float)(clock64() - t_loop0) + (i_begin > 0 ? A.cycles_s[item] : 0.f);
-            const float left = (float)(iterations - i) * (spent / (float)i) * (1.0f / 16384.0f);
-            s_item[0] = (left < 65535.f ? (int)left : 65535);
-            s_item[1] = queue_head_remaining(A) > s_item[0] ? 1 : 0;
-        }
+        // (ordering by measured time left instead - substeps left x this action's cycles per substep - was tried and is
+        // worse: the FIFO of waiting cloths stays sorted by substeps left, not by such estimates, and long cloths starve)
+        if (tid == 0) { s_item[0] = iterations - i; s_item[1] = queue_head_remaining(A) > iterations - i ? 1 : 0; }
         c.sync();
         const bool yield = s_item[1] != 0;
         const int left_units = s_item[0];
@@ -238,10 +233,8 @@ static __global__ void queue_init_kernel(int n, const unsigned long long *keys, 
                                          int *ngrab_s, float *cycles_s) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) {
-        // plan_work_kernel's key, after the sort: planned substeps; time left at a typical 1.2e5 cycles per substep,
-        // in the queue's units of 2^14 cycles
-        const float work = __uint_as_float(~(unsigned)(keys[j] >> 32));
-        const unsigned rem = (unsigned)fminf(fmaxf(work * (1.2e5f / 16384.0f), 0.f), 65535.f);
+        const float work = __uint_as_float(~(unsigned)(keys[j] >> 32));      // plan_work_kernel's key, after the sort: planned substeps
+        const unsigned rem = (unsigned)fminf(fmaxf(work, 0.f), 65535.f);
         queue[j] = ((unsigned long long)(unsigned)(j + 1) << 32) | (rem << 16) | (unsigned)j;
         progress[j] = 0; ngrab_s[j] = -1; cycles_s[j] = 0.f;
     }
@@ -481,17 +474,28 @@ template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevPar
         if (nt == 256) return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
         return launch_step_inst<T, 512, WC, RT, COL>(P, A, st);
     }
-    if (COL) {        // the coloured mode has no single-warp phases: two sizes are enough
-        if (nt == 256) return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
-        return launch_step_inst<T, 128, WC, RT, COL>(P, A, st);
-    }
-    switch (nt) {
-        case 32: return launch_step_inst<T, 32, WC, RT, COL>(P, A, st);
-        case 64: return launch_step_inst<T, 64, WC, RT, COL>(P, A, st);
-        case 256: return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
-        default: return launch_step_inst<T, 128, WC, RT, COL>(P, A, st);
-    }
+    if (nt == 256) return launch_step_inst<T, 256, WC, RT, COL>(P, A, st);
+    return launch_step_inst<T, 128, WC, RT, COL>(P, A, st);
 }
+
+// One (scalar type, compile-time grid width) pair per translation unit (cloth_inst.cu, built six times in
+// parallel): the kernel is one large force-inlined function and a single TU holding every variant compiles for
+// a quarter of an hour.
+template <typename T, int WC> int launch_step_wc(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st, bool rt, bool coloured) {
+    if (coloured) {
+        if constexpr (WC != 0) return rt ? launch_step_nt<T, WC, true, true>(P, A, st) : launch_step_nt<T, WC, false, true>(P, A, st);
+        else return CLOTHB200_ERR_UNSUPPORTED;   // coloured mode is built for the 25x25 and 64x64 grids
+    }
+    return rt ? launch_step_nt<T, WC, true, false>(P, A, st) : launch_step_nt<T, WC, false, false>(P, A, st);
+}
+#ifdef CLOTH_INSTANTIATE_WC
+template int launch_step_wc<CLOTH_T, CLOTH_INSTANTIATE_WC>(const DevParams<CLOTH_T> &, const StepArgs<CLOTH_T> &, cudaStream_t, bool, bool);
+#else
+#define CLOTH_EXTERN_WC(T, WC) extern template int launch_step_wc<T, WC>(const DevParams<T> &, const StepArgs<T> &, cudaStream_t, bool, bool);
+CLOTH_EXTERN_WC(float, 0) CLOTH_EXTERN_WC(float, 25) CLOTH_EXTERN_WC(float, 64)
+CLOTH_EXTERN_WC(double, 0) CLOTH_EXTERN_WC(double, 25) CLOTH_EXTERN_WC(double, 64)
+#undef CLOTH_EXTERN_WC
+#endif
 
 template <typename T> int launch_step(const ClothB200Params &hp, const StepArgs<T> &A, cudaStream_t st, int rmode = 0) {
     if (A.n_env == 0) return CLOTHB200_OK;
@@ -500,21 +504,10 @@ template <typename T> int launch_step(const ClothB200Params &hp, const StepArgs<
     if (P.N >= 32768) return CLOTHB200_ERR_UNSUPPORTED;   // 15-bit slots / 16-bit indices
     const bool rt = A.rest != nullptr;
     if (!rt && sizeof(T) == 8 && rmode == 0) return CLOTHB200_ERR_ARG;  // the parity build always takes the exact rest table
-    if (rmode == CLOTHB200_MODE_COLOURED) {
-        if (P.W == 25 && P.H == 25) return rt ? launch_step_nt<T, 25, true, true>(P, A, st) : launch_step_nt<T, 25, false, true>(P, A, st);
-        if (P.W == 64 && P.H == 64) return rt ? launch_step_nt<T, 64, true, true>(P, A, st) : launch_step_nt<T, 64, false, true>(P, A, st);
-        return CLOTHB200_ERR_UNSUPPORTED;   // coloured mode is built for the 25x25 and 64x64 grids
-    }
-    if (P.W == 25 && P.H == 25) {
-        if (rt) return launch_step_nt<T, 25, true, false>(P, A, st);
-        return launch_step_nt<T, 25, false, false>(P, A, st);
-    }
-    if (P.W == 64 && P.H == 64) {
-        if (rt) return launch_step_nt<T, 64, true, false>(P, A, st);
-        return launch_step_nt<T, 64, false, false>(P, A, st);
-    }
-    if (rt) return launch_step_nt<T, 0, true, false>(P, A, st);
-    return launch_step_nt<T, 0, false, false>(P, A, st);
+    const bool coloured = rmode == CLOTHB200_MODE_COLOURED;
+    if (P.W == 25 && P.H == 25) return launch_step_wc<T, 25>(P, A, st, rt, coloured);
+    if (P.W == 64 && P.H == 64) return launch_step_wc<T, 64>(P, A, st, rt, coloured);
+    return launch_step_wc<T, 0>(P, A, st, rt, coloured);
 }
 
 template <typename T> size_t step_smem_bytes(const ClothB200Params &hp) {
