@@ -156,6 +156,7 @@ def run_ours(args):
         restart_done(W + t)
     ev[1].record()
     barrier()
+    busy_cycles = (c.cost.double() * c.sim_steps.double()).clone()      # last timed launch: SM cycles each cloth was worked on
     launches = lib.clothb200_launch_count() - launches0
     elapsed_ms = ev[0].elapsed_time(ev[1])
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_ms_events)
@@ -222,7 +223,8 @@ def run_ours(args):
                        "restart from that pool" % reset_s,
                        "l2_flush": "256 MiB buffer written between timed iterations",
                        "l2": "per-step working set = %d MiB of state written+read once per launch (cloths live in shared memory "
-                             "for the whole action; HBM/L2 see one load and one store per env-step)" % (n * 20000 // 2 ** 20)},
+                             "while they are worked on; HBM/L2 see one load and one store per env-step plus 40 KB per swap of the "
+                             "time-sliced launch)" % (n * 20000 // 2 ** 20)},
             "substeps_per_s": sub_per_s, "substeps_per_env_step": total_substeps / (n_total * K),
             "e2e": {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / K},
@@ -242,6 +244,13 @@ def run_ours(args):
                              "frac": (n * K / (kernel_ms * 1e-3)) * HBM_B_PER_ENV_STEP / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src},
             "mean_coverage": float(cov_stats[0].item() / cov_stats[1].item()),
         }
+        # why a launch takes as long as it does: it cannot end before its slowest cloth nor before total work / resident slots
+        mhz = float(clocks.get("sm_mhz") or 1965.0)
+        slots = ctas.value * torch.cuda.get_device_properties(c.device).multi_processor_count
+        line["launch_balance"] = {"slowest_cloth_ms": float(busy_cycles.max().item()) / (mhz * 1e3),
+                                  "work_per_slot_ms": float(busy_cycles.sum().item()) / (mhz * 1e3) / slots,
+                                  "active_cloths": int((busy_cycles > 0).sum().item()), "resident_slots": int(slots),
+                                  "note": "rank 0, last timed launch; cycles spent inside the substep loop only"}
         if world == 1 and not args.no_extras:
             line["other_builds"] = other_builds(args, pool, dev_actions[W:W + 2])
         if world == 1 and not args.no_cpu_baseline:

@@ -18,7 +18,8 @@ void set_cuda_error(cudaError_t e, const char *where);
 // The action kernel: one CTA = one cloth = one whole ClothEnv.step (or n bare updates).
 // ------------------------------------------------------------------------------------------------
 // f32, 128 threads: eight cloths per SM need <= 64 registers per thread (the shared-memory footprint allows exactly eight)
-template <typename T, int NT> struct MinBlocks { static constexpr int v = (sizeof(T) == 4 && NT == 128) ? 8 : 1; };
+// (f64: four per SM by shared memory -> 128 registers)
+template <typename T, int NT> struct MinBlocks { static constexpr int v = NT == 128 ? (sizeof(T) == 4 ? 8 : 4) : 1; };
 template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED>
 __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(const __grid_constant__ DevParams<T> P, const __grid_constant__ StepArgs<T> A) {
     typedef ClothCTA<T, NT, WC, REST_TABLE, COLOURED> CTA;
