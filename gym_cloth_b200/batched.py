@@ -46,7 +46,7 @@ class BatchedCloth(object):
         self.num_steps = z(n); self.num_sim_steps = z(n)
         self.reward = z(n, dt=torch.float64); self.done = z(n)
         self.plans = torch.zeros(n, C.sizeof(_l.Plan), dtype=torch.uint8, device=dev)
-        # longest-first scheduling state: measured cycles/substep per env + scratch for the on-device sort
+        # measured cycles/substep per env (diagnostics) + scratch for the on-device launch order and the time-sliced queue
         self.cost = torch.zeros(n, dtype=torch.float32, device=dev)
         self.sched_scratch = torch.zeros(int(self.L.clothb200_sched_scratch_bytes(max(n, 1))), dtype=torch.uint8, device=dev)
         self.schedule = True

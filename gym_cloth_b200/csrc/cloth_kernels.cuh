@@ -466,7 +466,7 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
     return CLOTHB200_OK;
 }
 
-int slice_substeps();           // cloth_abi.cu: CLOTHB200_SLICE env var; default 128, 0 = whole actions
+int slice_substeps();           // cloth_abi.cu: CLOTHB200_SLICE env var; default 64, 0 = whole actions
 int threads_per_cloth(int W);   // cloth_abi.cu: CLOTHB200_NT env var; default 128 (512 for 64x64)
 
 template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
