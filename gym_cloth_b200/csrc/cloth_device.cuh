@@ -154,15 +154,21 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---- work queue of the time-sliced step kernel (one thread per CTA calls these) ----
-// At most qcap items are alive, each at most once in the queue, so ticket t and ticket t + qcap can share a slot:
-// t + qcap can only be issued after the holder of t has read its slot (that cloth must be re-queued first).
+// A ring of qcap slots; ticket t lives in slot t % qcap, tagged t + 1 (0 = empty).  At most qcap cloths are alive,
+// but a slot can still be wanted by ticket t + qcap while the holder of ticket t has not read it yet (the other
+// cloths can be re-queued in the meantime), so the reader empties the slot and the writer waits for an empty slot.
+// Every wait is for an event of a strictly older ticket held by a running CTA: no cycle.
 template <typename A_t> __device__ __forceinline__ int queue_pop(const A_t &A) {
     const int t = atomicAdd(&A.qctl[0], 1);
     volatile unsigned long long *slot = A.queue + (t % A.qcap);
     volatile int *done = A.qctl + 2;
     for (;;) {
         const unsigned long long v = *slot;
-        if ((int)(v >> 32) == t + 1) { __threadfence(); return (int)(v & 0xffffull); }
+        if ((int)(v >> 32) == t + 1) {
+            __threadfence();
+            *slot = 0ull;
+            return (int)(v & 0xffffull);
+        }
         if (*done >= A.qcap) return -1;
         __nanosleep(200);
     }
@@ -171,6 +177,8 @@ template <typename A_t> __device__ __forceinline__ void queue_push(const A_t &A,
     __threadfence();
     const int t = atomicAdd(&A.qctl[1], 1);
     const unsigned rem = (unsigned)(remaining > 65535 ? 65535 : remaining);
+    volatile unsigned long long *slot = A.queue + (t % A.qcap);
+    while (*slot != 0ull) __nanosleep(100);
     atomicExch(A.queue + (t % A.qcap), ((unsigned long long)(unsigned)(t + 1) << 32) | (rem << 16) | (unsigned)item);
 }
 // substeps left of the cloth at the head of the queue (0 if nothing is waiting); a racy peek, only a heuristic

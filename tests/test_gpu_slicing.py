@@ -61,6 +61,9 @@ def test_sliced_f32_matches_unsliced():
         for k in ("sim", "ngrab", "mask", "done"):
             assert np.array_equal(r[k], g[k]), k
         assert np.array_equal(r["pos"], g["pos"]) and np.array_equal(r["rew"], g["rew"])
+    # queue stress: two-substep slices on four slots = ~20 000 swaps through a 24-slot ring
+    hammer = _run("f32", n, True, acts[:1], slots=4, q=2)
+    assert np.array_equal(ref[0]["pos"], hammer[0]["pos"]) and np.array_equal(ref[0]["sim"], hammer[0]["sim"])
 
 
 def test_sliced_tear_and_tier2_rest_lengths():
