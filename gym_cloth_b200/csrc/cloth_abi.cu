@@ -332,6 +332,7 @@ int clothb200_params_validate(const ClothB200Params *p) {
     if (p->num_width_points * p->num_height_points >= 32768) return CLOTHB200_ERR_UNSUPPORTED;
     if (!(p->thickness > 0) || !(p->density > 0) || p->frames_per_sec <= 0 || p->simulation_steps <= 0) return CLOTHB200_ERR_CONFIG;
     if (!(p->gripper_height / p->thickness < 4096)) return CLOTHB200_ERR_UNSUPPORTED;
+    if (p->reward_type != CLOTHB200_REWARD_COVERAGE_DELTA && p->reward_type != CLOTHB200_REWARD_COVERAGE) return CLOTHB200_ERR_CONFIG;
     return CLOTHB200_OK;
 }
 
@@ -351,6 +352,13 @@ int clothb200_decode_actions_host(const ClothB200Params *P, int n_env, const dou
     else { lo[0] = -0.25; lo[1] = -0.25; lo[2] = 0.0; lo[3] = -pi_f32; hi[0] = 1.25; hi[1] = 1.25; hi[2] = 1.0; hi[3] = pi_f32; }
     for (int e = 0; e < n_env; e++) {
         const double *a = actions + 4 * e;
+        if (a[0] != a[0] || a[1] != a[1] || a[2] != a[2] || a[3] != a[3]) {
+            // NaN survives np.clip and the reference's `while True: current_l += ...; if current_l >= total` loop
+            // (cloth_env.py:462-467) would never exit: the plan is marked bad, the step does nothing and reports BADSTATE
+            plans[e].gx = 0.5; plans[e].gy = 0.5; plans[e].dxr = 0.0; plans[e].dyr = 0.0; plans[e].iters_pull = 0;
+            plans[e].reserved = CLOTHB200_PLAN_BAD_ACTION;
+            continue;
+        }
         double x = clampd(a[0], lo[0], hi[0]), y = clampd(a[1], lo[1], hi[1]);
         const double a2 = clampd(a[2], lo[2], hi[2]), a3 = clampd(a[3], lo[3], hi[3]);
         double length = a2, radians = a3;
@@ -368,7 +376,7 @@ int clothb200_decode_actions_host(const ClothB200Params *P, int n_env, const dou
         if (P->delta_actions) {
             const double stepl = sqrt(pow(xr, 2.0) + pow(yr, 2.0));
             int ii = 0;
-            if (stepl > 0.0) { double cur = 0; for (;;) { cur += stepl; if (cur >= total) break; ii += 1; } }
+            if (stepl > 0.0) { double cur = 0; for (;;) { cur += stepl; if (cur >= total || ii >= CLOTHB200_MAX_ITERS_PULL) break; ii += 1; } }
             ip = ii;
         } else ip = (int)(P->iters_pull_max * length);
         plans[e].gx = x; plans[e].gy = y; plans[e].dxr = xr; plans[e].dyr = yr; plans[e].iters_pull = ip; plans[e].reserved = 0;

@@ -66,6 +66,7 @@ template <typename T> struct DevParams {
     const uint32_t *sweep_tbl;
     int sweep_levels, sweep_lw, sweep_thresh;
     int relax_iters;             // coloured mode: limit passes per update (>= 1; the reference does exactly one)
+    int reward_abs;              // reward_type 'coverage': rew += coverage, not its delta (cloth_env.py:657-659)
     int force_grab;              // cfg env.force_grab: grow the grip radius by 0.02 until something is gripped (cloth_env.py:434-444)
 };
 
@@ -162,6 +163,7 @@ template <typename A_t> __device__ __forceinline__ int queue_pop(const A_t &A) {
     const int t = atomicAdd(&A.qctl[0], 1);
     volatile unsigned long long *slot = A.queue + (t % A.qcap);
     volatile int *done = A.qctl + 2;
+    unsigned ns = 100u;
     for (;;) {
         const unsigned long long v = *slot;
         if ((int)(v >> 32) == t + 1) {
@@ -170,7 +172,8 @@ template <typename A_t> __device__ __forceinline__ int queue_pop(const A_t &A) {
             return (int)(v & 0xffffull);
         }
         if (*done >= A.qcap) return -1;
-        __nanosleep(200);
+        __nanosleep(ns);                      // idle slots at the end of a launch: back off, the SM belongs to the working cloths
+        if (ns < 4000u) ns += ns;
     }
 }
 template <typename A_t> __device__ __forceinline__ void queue_push(const A_t &A, int item, int remaining) {
@@ -316,6 +319,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // swaps it in after the barrier, when no thread reads old positions any more.
     __device__ __forceinline__ void hooke_verlet() {
         int bad = 0;
+        if (!COLOURED && tid < 2 * NCLS) size_count()[tid] = 0;     // work-list size classes of this substep (lstB is idle here)
         for (int p = tid; p < N; p += NT) {
             const P4 Pp = pos[p];
             if (Pp.w != T(0)) continue;  // pinned: Verlet skips it, its force is never used
@@ -361,8 +365,19 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         if (!(f > T(-1048576) && f < T(1048576))) { misc[3] = 1; f = T(0); }  // NaN/huge: reference raises
         return (int)f;
     }
+    // Ordered scatter (reference-order mode, compile-time grids of <= 1023 points run by 4 warps): the points are dealt
+    // to the warps in contiguous index chunks, pass 1 counts per (bucket, warp) in the four bytes of tinfo[slot], pass 2
+    // turns the counts into one list cursor per warp, and in pass 3 every warp appends its chunk row by row in lane
+    // order - so every bucket list comes out in point-index order (the dict value order of cloth.pyx:301-305) and
+    // nothing has to be ranked or permuted afterwards.
+    static constexpr int CHUNK = (((WC * WC + NWARPS - 1) / NWARPS) + 31) & ~31;
+    static constexpr bool ORDERED = !COLOURED && WC != 0 && NWARPS == 4 && WC * WC <= 1023 && CHUNK <= 255;
+    static constexpr int HASH_ROWS = ORDERED ? CHUNK / 32 : 0;
     __device__ __forceinline__ void commit_and_hash() {
-        for (int p = tid; p < N; p += NT) {
+        const int nrows = ORDERED ? HASH_ROWS : (N + NT - 1) / NT;
+        for (int i = 0; i < nrows; i++) {
+            const int p = ORDERED ? warp * CHUNK + 32 * i + lane : tid + i * NT;
+            if (p >= N) continue;
             P4 Pp = pos[p];
             if (Pp.w == T(0)) {
                 const P4 Nw = prev[p];
@@ -385,7 +400,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                 if (probes > (int)msk) { misc[3] = 1; break; }
                 slot = (slot + 1) & msk;
             }
-            const uint32_t r = atomicAdd(&tinfo[slot], 1u);
+            const uint32_t r = atomicAdd(&tinfo[slot], ORDERED ? 1u << (8 * warp) : 1u);
             pslot[p] = (uint16_t)(slot | (r == 0 ? 0x8000u : 0u));
         }
     }
@@ -461,27 +476,13 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         T cx = gx - Q.x, cy = gy - Q.y, cz = gz - Q.z;
         pos[p] = mk4(Q.x + cx * P.fric1, Q.y + cy * P.fric1, Q.z + cz * P.fric1, Pp.w);
     }
-    // buckets whose snapshot has a hit are queued for the ordered replay (by their first hit point's owner);
-    // points of buckets without any hit are final and get their plane collision here.
-    __device__ __forceinline__ void collide_queue_and_plane() {
-        for (int p = tid; p < N; p += NT) {
-            const P4 Pp = pos[p];
-            if (Pp.w != T(0)) continue;
-            const uint32_t slot = pslot[p] & 0x7fffu;
-            const int first = tkey[slot];
-            // A bucket with a hit is finished by collide_replay(), plane collision included: its members must keep
-            // their pre-plane positions while the replay reads them.
-            if (first == CLOTH_FIRST_NONE) plane_point(p);
-            else if (first == p) lstA[atomicAdd(&misc[1], 1)] = (uint16_t)slot;
-        }
-    }
     // ordered replay of one bucket by one warp: from the first hit point on (nothing before it moved, so its
     // own evaluation equals the snapshot), in index order; contributions are summed in candidate order.
     // A bucket of up to 32*K members replayed out of registers: lane l keeps members l, l+32, ... (bucket lists are
     // in point-index order, so walking register set 0, then 1, ... visits the subjects in the reference's order and
     // the per-set ballots add the contributions in candidate order).  Crumpled cloths pile 40-100 points into one
     // cell; the shared-memory path below costs them 4x more per member.
-    template <int K> __device__ __forceinline__ void replay_bucket_regs(const int start, const int cnt, const int j0) {
+    template <int K> __device__ __forceinline__ void replay_bucket_regs(const uint16_t *lstB, const int start, const int cnt, const int j0) {
         int mine[K];
         P4 Pm[K];
         bool dirty[K];
@@ -559,133 +560,296 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         }
     }
 
-    __device__ __forceinline__ void collide_replay() {
+    // ==================================================================================================
+    // Reference-order self-collision, bucket-centric.  self_collide (cloth.pyx:313-343) is sequential only inside one
+    // cell, so every cell with >= 2 points is one unit of work: its members sit in the lanes of a warp in point-index
+    // order (the dict value order of cloth.pyx:301-305), subject j is broadcast with shuffles, all candidates are
+    // tested at once, the hits are summed in candidate order and lane j takes the correction before subject j+1 is
+    // looked at.  Cells are small (9 points on a flat cloth), so consecutive cells of the work list are packed side
+    // by side into the 32 lanes ("segments") and advance in lock step.  No snapshot pre-test, no per-point gather.
+    // ==================================================================================================
+    // The work list is kept sorted by bucket size, largest first (a counting sort over the size classes 2..32 and
+    // "more than 32"): lock-stepped segments then have similar lengths, and the piles, which take longest, start first.
+    // Class counters live at the head of lstB, which is idle until collide_buckets(); hooke_verlet() zeroes them.
+    // The list itself: behind the counters (ordered scatter: lstB has no other use) or in the key area (dead after pass 1).
+    static constexpr int NCLS = 34;                                  // class = min(cnt, 33); 0 and 1 unused
+    __device__ __forceinline__ int *size_count() const { return reinterpret_cast<int *>(lstB); }
+    __device__ __forceinline__ int *size_fill() const { return reinterpret_cast<int *>(lstB) + NCLS; }
+    __device__ __forceinline__ uint16_t *worklist() const { return ORDERED ? lstB + 4 * NCLS : reinterpret_cast<uint16_t *>(tkey); }
+    // member list of the buckets in point-index order
+    __device__ __forceinline__ const uint16_t *ordered_list() const { return ORDERED ? lstA : lstB; }
+    // tinfo[slot] after pass 2.  Unordered scatter: cnt | (end offset << 16), the high half running from start to end
+    // during pass 3.  Ordered scatter: cnt | start << 10 | warp 0's cursor << 20, the cursors of warps 1-3 in tkey[slot].
+    __device__ __forceinline__ void bucket_range(uint32_t info, int &cnt, int &start) const {
+        if (ORDERED) { cnt = (int)(info & 1023u); start = (int)((info >> 10) & 1023u); }
+        else { cnt = (int)(info & 0xffffu); start = (int)(info >> 16) - cnt; }
+    }
+    // pass 2: the first arriver of each bucket reserves its range and counts the bucket in its size class
+    __device__ __forceinline__ void alloc_buckets_ro() {
+        int *szc = size_count();
+        for (int p = tid; p < N; p += NT) {
+            const uint32_t s = pslot[p];
+            if (s & 0x8000u) {
+                const uint32_t slot = s & 0x7fffu;
+                const uint32_t info = tinfo[slot];
+                uint32_t cnt = info;
+                if (ORDERED) cnt = (info & 255u) + ((info >> 8) & 255u) + ((info >> 16) & 255u) + (info >> 24);
+                const uint32_t off = (uint32_t)atomicAdd(&misc[0], (int)cnt);
+                if (ORDERED) {
+                    const uint32_t c1 = off + (info & 255u), c2 = c1 + ((info >> 8) & 255u), c3 = c2 + ((info >> 16) & 255u);
+                    tinfo[slot] = cnt | (off << 10) | (off << 20);
+                    tkey[slot] = (int)(c1 | (c2 << 10) | (c3 << 20));
+                } else {
+                    tinfo[slot] = cnt | (off << 16);
+                }
+                if (cnt > 1u) atomicAdd(&szc[cnt < 33u ? cnt : 33u], 1);
+            }
+        }
+    }
+    // pass 3: scatter of the members; the first arriver also files the bucket in the sorted work list.
+    // A point alone in its cell cannot collide and gets its plane collision right away.
+    __device__ __forceinline__ void scatter_members_ro() {
+        const unsigned FULL = 0xffffffffu;
+        uint16_t *wl = worklist();
+        int *szf = size_fill();
+        // every warp scans the class counters itself (lane l <-> class 33 - l): first work-list index of each class
+        int cls_off = size_count()[33 - lane];                       // classes 33 .. 2
+        {
+            int incl = cls_off;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            if (tid == 31) misc[1] = incl;                           // number of buckets with >= 2 members
+            cls_off = incl - cls_off;
+        }
+        const int nrows = ORDERED ? HASH_ROWS : (N + NT - 1) / NT;
+        for (int i = 0; i < nrows; i++) {
+            const int p = ORDERED ? warp * CHUNK + 32 * i + lane : tid + i * NT;
+            const bool on = p < N;
+            uint32_t s = 0u, cnt = 0u, at = 0u;
+            if (ORDERED) {
+                s = on ? pslot[p] : 0u;
+                const uint32_t slot = s & 0x7fffu;
+                // the lanes of this row that share my bucket, in lane (= point index) order
+                const unsigned peers = __match_any_sync(FULL, on ? slot : 0x10000u + lane);
+                const int leader = __ffs(peers) - 1;
+                uint32_t cur = 0u;
+                if (on && lane == leader) {
+                    const uint32_t n = (uint32_t)__popc(peers);
+                    if (warp == 0) cur = atomicAdd(&tinfo[slot], n << 20) >> 20;
+                    else cur = ((uint32_t)atomicAdd(&tkey[slot], (int)(n << (10 * (warp - 1)))) >> (10 * (warp - 1))) & 1023u;
+                }
+                cur = __shfl_sync(FULL, cur, leader);
+                at = (cur & 1023u) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+                cnt = on ? (tinfo[slot] & 1023u) : 0u;
+            } else if (on) {
+                s = pslot[p];
+                const uint32_t old = atomicAdd(&tinfo[s & 0x7fffu], 0x10000u);
+                cnt = old & 0xffffu; at = old >> 16;
+            }
+            const bool files = on && (s & 0x8000u) && cnt > 1u;
+            const int cls = files ? (cnt < 33u ? (int)cnt : 33) : 33;
+            const int off = __shfl_sync(FULL, cls_off, 33 - cls);
+            if (files) wl[off + atomicAdd(&szf[cls], 1)] = (uint16_t)(s & 0x7fffu);
+            if (on) {
+                if (cnt == 1u) plane_point(p);
+                else lstA[at] = (uint16_t)p;
+            }
+        }
+    }
+    // index-ordered copy of a bucket of any size: lstA[start..start+cnt) -> lstB (one warp)
+    __device__ __forceinline__ void order_bucket(const int start, const int cnt) {
+        for (int base = 0; base < cnt; base += 32) {
+            const bool on = base + lane < cnt;
+            const int mine = on ? lstA[start + base + lane] : 0;
+            int rk = 0;
+            for (int cb = 0; cb < cnt; cb += 32) {
+                const int oth = cb + lane < cnt ? lstA[start + cb + lane] : 0x7fffffff;
+                const int nj = min(32, cnt - cb);
+                for (int j = 0; j < nj; j++) rk += __shfl_sync(0xffffffffu, oth, j) < mine ? 1 : 0;
+            }
+            if (on) lstB[start + rk] = (uint16_t)mine;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void collide_buckets() {
+        const unsigned FULL = 0xffffffffu;
         for (int j = tid; j < P.ev_words; j += NT) ev[j] = 0u;   // pslot is dead from here on: its storage becomes the spring queue
         const int nwork = misc[1];
+        const uint16_t *wl = worklist();
+        const uint16_t *lst = ordered_list();
+        int badq = 0;                                            // coincident points (reference: ZeroDivisionError)
+        long long tw = prof_on ? clock64() : 0;
         for (;;) {
-            int wi = 0;
-            if (lane == 0) wi = atomicAdd(&misc[6], 1);     // buckets are handed out dynamically: their sizes vary a lot
-            wi = __shfl_sync(0xffffffffu, wi, 0);
-            if (wi >= nwork) break;
-            const uint32_t slot = lstA[wi];
-            const uint32_t info = tinfo[slot];
-            const int cnt = info & 0xffffu, start = (int)(info >> 16) - cnt;
-            const int first = tkey[slot];
-            int j0 = 0;
-            for (int base = 0; base < cnt; base += 32) {
-                const int j = base + lane;
-                const unsigned m = __ballot_sync(0xffffffffu, j < cnt && lstB[start + j] == first);
-                if (m) { j0 = base + __ffs(m) - 1; break; }
+            // ---- take the longest run of work-list buckets that fits the 32 lanes (one bucket if it is larger) ----
+            int cur = 0;
+            if (lane == 0) cur = *(volatile int *)&misc[6];
+            cur = __shfl_sync(FULL, cur, 0);
+            int k = 0, cnt_i = 0, start_i = 0, incl = 0;
+            for (;;) {
+                if (cur >= nwork) break;
+                const int item = cur + lane;
+                cnt_i = 64; start_i = 0;
+                if (item < nwork) bucket_range(tinfo[wl[item]], cnt_i, start_i);
+                incl = min(cnt_i, 64);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                k = __popc(__ballot_sync(FULL, incl <= 32));     // prefix sums are increasing: the fitting items are a prefix
+                int old = 0;
+                if (lane == 0) old = atomicCAS(&misc[6], cur, cur + (k ? k : 1));
+                old = __shfl_sync(FULL, old, 0);
+                if (old == cur) break;
+                cur = old;
             }
-            if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[cnt <= 32 ? 14 : 15], (unsigned long long)(cnt - j0)); if (cnt > 32) atomicAdd((unsigned long long *)&pacc[5], 1ull); }
-            if (cnt <= 32) {
-                // common case: the bucket fits the warp.  Lane l keeps member l's position in registers; the point
-                // being replayed is broadcast with shuffles, so a step costs no shared-memory round trip.
-                const int mine = lane < cnt ? lstB[start + lane] : 0;
-                P4 Pm = pos[mine];
-                bool dirty = false;
-                // pinned members never move and are skipped as subjects (cloth.pyx:314-315)
-                unsigned todo = __ballot_sync(0xffffffffu, lane < cnt && lane >= j0 && Pm.w == T(0));
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const T px = __shfl_sync(0xffffffffu, Pm.x, j), py = __shfl_sync(0xffffffffu, Pm.y, j),
-                            pz = __shfl_sync(0xffffffffu, Pm.z, j);
-                    const T d0 = px - Pm.x, d1 = py - Pm.y, d2 = pz - Pm.z;
-                    const T qq = d0 * d0 + d1 * d1 + d2 * d2;
-                    const bool hit = lane < cnt && lane != j && within_thresh(qq);
-                    unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m) {
-                        T c0 = T(0), c1 = T(0), c2 = T(0);
-                        if (hit) {
-                            if (qq == T(0)) misc[3] = 1;
-                            T factor;
-                            if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
-                            else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
-                            c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
-                        }
-                        const int n = __popc(m);
-                        T t0 = T(0), t1 = T(0), t2 = T(0);
-                        while (m) {
-                            const int l = __ffs(m) - 1;
-                            m &= m - 1;
-                            t0 += __shfl_sync(0xffffffffu, c0, l);
-                            t1 += __shfl_sync(0xffffffffu, c1, l);
-                            t2 += __shfl_sync(0xffffffffu, c2, l);
-                        }
+            if (cur >= nwork) break;
+            if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[4], (unsigned long long)(t - tw)); tw = t; }
+            if (k == 0) {
+                // a pile of more than 32 points: members in 2 or 4 registers per lane, or the shared-memory path
+                const int cnt = __shfl_sync(FULL, cnt_i, 0), start = __shfl_sync(FULL, start_i, 0);
+                if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)cnt); atomicAdd((unsigned long long *)&pacc[5], 1ull); }
+                if (!ORDERED) order_bucket(start, cnt);
+                if (cnt <= 64) replay_bucket_regs<2>(lst, start, cnt, 0);
+                else if (cnt <= 128) replay_bucket_regs<4>(lst, start, cnt, 0);
+                else replay_bucket_smem(lst, start, cnt, 0);
+                __syncwarp();
+                if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[6], (unsigned long long)(t - tw)); tw = t; }
+                continue;
+            }
+            // ---- lane -> (segment, member) ----
+            const unsigned ends = __reduce_or_sync(FULL, lane < k ? 1u << (incl - 1) : 0u);   // last lane of every segment
+            const int total = __shfl_sync(FULL, incl, k - 1);
+            const int my_i = __popc(ends & ((1u << lane) - 1u));
+            const int s_end = __shfl_sync(FULL, incl, my_i), s_cnt = __shfl_sync(FULL, cnt_i, my_i), s_start = __shfl_sync(FULL, start_i, my_i);
+            const bool valid = lane < total;
+            const int seg_cnt = valid ? s_cnt : 0, seg_base = valid ? s_end - s_cnt : 0, li = lane - seg_base;
+            const int maxcnt = __reduce_max_sync(FULL, seg_cnt);
+            if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[14], (unsigned long long)total); atomicAdd((unsigned long long *)&pacc[11], (unsigned long long)k); }
+            int mine = valid ? lstA[s_start + li] : 0;
+            if (!ORDERED) {
+                // members into point-index order: rank inside the segment, permute through the bucket's lstB range
+                // (the scatter often leaves a bucket sorted already: one compare with the left neighbour tells)
+                const int left = __shfl_up_sync(FULL, mine, 1);
+                if (__any_sync(FULL, valid && li > 0 && left > mine)) {
+                    int rk = 0;
+#pragma unroll 1
+                    for (int j = 0; j < maxcnt; j++) {
+                        const int oth = __shfl_sync(FULL, mine, seg_base + j);
+                        rk += (j < seg_cnt && oth < mine) ? 1 : 0;
+                    }
+                    if (valid) lstB[s_start + rk] = (uint16_t)mine;
+                    __syncwarp();
+                    if (valid) mine = lstB[s_start + li];
+                }
+            }
+            P4 Pm = pos[mine];
+            bool dirty = false;
+            const unsigned segmask = seg_cnt >= 32 ? FULL : ((1u << seg_cnt) - 1u);
+            // bit j <=> member j of my segment is a subject I am a candidate for: it exists, is not pinned (pinned
+            // members never move and are skipped as subjects, cloth.pyx:314-315) and is not me
+            const unsigned subj = (__ballot_sync(FULL, valid && Pm.w == T(0)) >> seg_base) & segmask & ~(1u << li);
+#pragma unroll 1
+            for (int j = 0; j < maxcnt; j++) {
+                const int src = seg_base + j;
+                const T px = __shfl_sync(FULL, Pm.x, src), py = __shfl_sync(FULL, Pm.y, src), pz = __shfl_sync(FULL, Pm.z, src);
+                const T d0 = px - Pm.x, d1 = py - Pm.y, d2 = pz - Pm.z;
+                const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                const bool hit = (subj & (1u << j)) && within_thresh(qq);
+                const unsigned m = __ballot_sync(FULL, hit);
+                if (m) {
+                    T c0 = T(0), c1 = T(0), c2 = T(0);
+                    if (hit) {
+                        badq |= qq == T(0) ? 1 : 0;
+                        T factor;
+                        if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                        else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                        c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
+                    }
+                    unsigned mm = (m >> seg_base) & segmask;        // hits of my segment's subject, bit = member
+                    const int n = __popc(mm);
+                    int rounds = __reduce_max_sync(FULL, n);
+                    T t0 = T(0), t1 = T(0), t2 = T(0);
+#pragma unroll 1
+                    do {                                            // candidate order
+                        const int l = seg_base + (mm ? __ffs(mm) - 1 : 0);
+                        const T v0 = __shfl_sync(FULL, c0, l), v1 = __shfl_sync(FULL, c1, l), v2 = __shfl_sync(FULL, c2, l);
+                        if (mm) { t0 += v0; t1 += v1; t2 += v2; }
+                        mm &= mm - 1u;
+                    } while (--rounds > 0);
+                    if (n && li == j) {
                         const T nf = (T)n;
                         T cx, cy, cz;
                         if (FAST) { const T inv = T(1) / (nf * P.sim_steps); cx = t0 * inv; cy = t1 * inv; cz = t2 * inv; }
                         else { cx = t0 / nf / P.sim_steps; cy = t1 / nf / P.sim_steps; cz = t2 / nf / P.sim_steps; }
-                        if (lane == j) { Pm = mk4(px + cx, py + cy, pz + cz, Pm.w); dirty = true; }
-                    }
-                }
-                if (lane < cnt) {
-                    // plane collision (cloth.pyx:345-370) of my member, then one write-back
-                    if (Pm.w == T(0) && !(Pm.z >= P.min_z)) {
-                        const P4 Q = prev[mine];
-                        T t = (P.min_z - Q.z) * T(1.0);
-                        T tx = Q.x + t * T(-0.0), ty = Q.y + t * T(-0.0), tz = Q.z + t * T(-1.0);
-                        T gx = tx + P.surf_off * T(0.0), gy = ty + P.surf_off * T(0.0), gz = tz + P.surf_off * T(1.0);
-                        T ex = gx - Q.x, ey = gy - Q.y, ez = gz - Q.z;
-                        Pm = mk4(Q.x + ex * P.fric1, Q.y + ey * P.fric1, Q.z + ez * P.fric1, Pm.w);
+                        Pm = mk4(px + cx, py + cy, pz + cz, Pm.w);
                         dirty = true;
                     }
-                    if (dirty) pos[mine] = Pm;
                 }
-            } else if (cnt <= 64) {
-                replay_bucket_regs<2>(start, cnt, j0);
-            } else if (cnt <= 128) {
-                replay_bucket_regs<4>(start, cnt, j0);
-            } else {
-                for (int j = j0; j < cnt; j++) {
-                    const int p = lstB[start + j];
-                    const P4 Pp = pos[p];
-                    if (Pp.w != T(0)) continue;
-                    T t0 = T(0), t1 = T(0), t2 = T(0);
-                    int n = 0;
-                    for (int base = 0; base < cnt; base += 32) {
-                        const int cj = base + lane;
-                        const bool valid = cj < cnt && cj != j;
-                        T c0 = T(0), c1 = T(0), c2 = T(0);
-                        bool hit = false;
-                        if (valid) {
-                            const P4 Pq = pos[lstB[start + cj]];
-                            const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
-                            const T qq = d0 * d0 + d1 * d1 + d2 * d2;
-                            if (within_thresh(qq)) {
-                                if (qq == T(0)) misc[3] = 1;
-                                else {
-                                    T factor;
-                                    if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
-                                    else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
-                                    c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
-                                    hit = true;
-                                }
-                            }
-                        }
-                        unsigned m = __ballot_sync(0xffffffffu, hit);
-                        n += __popc(m);
-                        while (m) {
-                            const int l = __ffs(m) - 1;
-                            m &= m - 1;
-                            t0 += __shfl_sync(0xffffffffu, c0, l);
-                            t1 += __shfl_sync(0xffffffffu, c1, l);
-                            t2 += __shfl_sync(0xffffffffu, c2, l);
+            }
+            if (valid) {
+                // plane collision (cloth.pyx:345-370) of my member, then one write-back
+                if (Pm.w == T(0) && !(Pm.z >= P.min_z)) {
+                    const P4 Q = prev[mine];
+                    T t = (P.min_z - Q.z) * T(1.0);
+                    T tx = Q.x + t * T(-0.0), ty = Q.y + t * T(-0.0), tz = Q.z + t * T(-1.0);
+                    T gx = tx + P.surf_off * T(0.0), gy = ty + P.surf_off * T(0.0), gz = tz + P.surf_off * T(1.0);
+                    T ex = gx - Q.x, ey = gy - Q.y, ez = gz - Q.z;
+                    Pm = mk4(Q.x + ex * P.fric1, Q.y + ey * P.fric1, Q.z + ez * P.fric1, Pm.w);
+                    dirty = true;
+                }
+                if (dirty) pos[mine] = Pm;
+            }
+            __syncwarp();
+            if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[6], (unsigned long long)(t - tw)); tw = t; }
+        }
+        if (badq) misc[3] = 1;
+    }
+
+    // a bucket of more than 128 points, replayed through shared memory (lstB ordered)
+    __device__ __forceinline__ void replay_bucket_smem(const uint16_t *lstB, const int start, const int cnt, const int j0) {
+        for (int j = j0; j < cnt; j++) {
+            const int p = lstB[start + j];
+            const P4 Pp = pos[p];
+            if (Pp.w != T(0)) continue;
+            T t0 = T(0), t1 = T(0), t2 = T(0);
+            int n = 0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int cj = base + lane;
+                const bool valid = cj < cnt && cj != j;
+                T c0 = T(0), c1 = T(0), c2 = T(0);
+                bool hit = false;
+                if (valid) {
+                    const P4 Pq = pos[lstB[start + cj]];
+                    const T d0 = Pp.x - Pq.x, d1 = Pp.y - Pq.y, d2 = Pp.z - Pq.z;
+                    const T qq = d0 * d0 + d1 * d1 + d2 * d2;
+                    if (within_thresh(qq)) {
+                        if (qq == T(0)) misc[3] = 1;
+                        else {
+                            T factor;
+                            if (FAST) factor = P.thresh * rsqrtf((float)qq) - T(1);
+                            else { const T d = sqrt_t(qq); factor = (P.thresh - d) / d; }
+                            c0 = d0 * factor; c1 = d1 * factor; c2 = d2 * factor;
+                            hit = true;
                         }
                     }
-                    if (n && lane == 0) {
-                        const T nf = (T)n;
-                        const T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
-                        pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
-                    }
-                    __syncwarp();
                 }
-                for (int base = 0; base < cnt; base += 32)
-                    if (base + lane < cnt) plane_point(lstB[start + base + lane]);
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                n += __popc(m);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    t0 += __shfl_sync(0xffffffffu, c0, l);
+                    t1 += __shfl_sync(0xffffffffu, c1, l);
+                    t2 += __shfl_sync(0xffffffffu, c2, l);
+                }
+            }
+            if (n && lane == 0) {
+                const T nf = (T)n;
+                const T cx = t0 / nf / P.sim_steps, cy = t1 / nf / P.sim_steps, cz = t2 / nf / P.sim_steps;
+                pos[p] = mk4(Pp.x + cx, Pp.y + cy, Pp.z + cz, Pp.w);
             }
             __syncwarp();
         }
+        for (int base = 0; base < cnt; base += 32)
+            if (base + lane < cnt) plane_point(lstB[start + base + lane]);
     }
 
     // ---- _limit_spring_changes (cloth.pyx:258-296) ----
@@ -1073,12 +1237,9 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         if (prof_on && tid == 0) plast = clock64();
         hooke_verlet();            sync(); ptick(0);
         commit_and_hash();         sync(); ptick(1);
-        alloc_buckets();           sync(); ptick(2);
-        scatter_members();         sync(); ptick(3);
-        order_and_snapshot();      sync(); ptick(4);
-        collide_queue_and_plane(); sync(); ptick(6);
-        if (prof_on && tid == 0) pacc[11] += misc[1];
-        collide_replay();          sync(); ptick(7);
+        alloc_buckets_ro();        sync(); ptick(2);
+        scatter_members_ro();      sync(); ptick(3);
+        collide_buckets();         sync(); ptick(7);
         limit_snapshot();          sync(); ptick(8);
         limit_resolve(rot % NWARPS);
         if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[6] = 0; }

@@ -85,9 +85,11 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
     const bool stepping = A.mode == KMODE_STEP;
     if (stepping) {
         const ClothB200Plan plan = A.plans[env];
-        if (i_begin > 0) ngrab = ngrab_in;            // resumed slice: the grip is part of the stored state
+        const bool bad_action = (plan.reserved & CLOTHB200_PLAN_BAD_ACTION) != 0;   // NaN action: nothing is gripped, BADSTATE
+        if (bad_action) { ngrab = 0; if (tid == 0) c.misc[3] = 1; }
+        else if (i_begin > 0) ngrab = ngrab_in;       // resumed slice: the grip is part of the stored state
         else ngrab = c.grab_top(plan.gx, plan.gy, P.grip_radius);
-        if (P.force_grab && i_begin == 0) {
+        if (P.force_grab && i_begin == 0 && !bad_action) {
             // cloth_env.py:434-444: `while len(grabbed_pts) == 0: grip_radius += 0.02; grab_top(...)` (radius restored afterwards).
             // A cloth with no point under z = height + 2*thickness can never be gripped; the reference would spin forever,
             // we stop once the cylinder covers any reachable (x, y) and report NOGRAB.
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
             A.progress[item] = i; A.ngrab_s[item] = ngrab;
             A.cycles_s[item] = (float)(clock64() - t_loop0) + (i_begin > 0 ? A.cycles_s[item] : 0.f);
             if (bad_now && A.flags) A.flags[env] = flags_in | CLOTHB200_FLAG_BADSTATE;
-            if (A.prof) for (int k = 0; k < 14; k++) A.prof[(size_t)env * 16 + k] += c.pacc[k];
+            if (A.prof) for (int k = 0; k < 16; k++) if (k != 10) A.prof[(size_t)env * 16 + k] += c.pacc[k];
             bulk_commit_wait_all();
             fence_async_all();
             queue_push(A, item, left_units);
@@ -205,9 +207,12 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
             if (ngrab == 0) rew += -0.01;
             if (cov > 0.92) rew += 5.;
             rew += 0.0;
-            const double prevc = A.prev_coverage[env];
-            rew += cov - prevc;
-            A.prev_coverage[env] = cov;
+            if (P.reward_abs) rew += cov;                         // 'coverage' (cloth_env.py:657-659): _prev_reward is left alone
+            else {                                                // 'coverage-delta' (cloth_env.py:660-662, compute_delta :640-643)
+                const double prevc = A.prev_coverage[env];
+                rew += cov - prevc;
+                A.prev_coverage[env] = cov;
+            }
             A.reward[env] = rew;
             A.done[env] = (steps >= P.max_actions) || tear || oob || (cov > 0.92);
         }
@@ -312,8 +317,10 @@ __global__ void decode_actions_kernel(int n, const T *__restrict__ actions, Clot
     else if (delta_actions) { lo[0] = 0; lo[1] = 0; lo[2] = -1; lo[3] = -1; hi[0] = hi[1] = hi[2] = hi[3] = 1; }
     else { lo[0] = -0.25; lo[1] = -0.25; lo[2] = 0.0; lo[3] = -pi_f32; hi[0] = 1.25; hi[1] = 1.25; hi[2] = 1.0; hi[3] = pi_f32; }
     double a[4];
+    bool nan_action = false;
     for (int i = 0; i < 4; i++) {
         double v = (double)actions[4 * e + i];
+        if (v != v) { nan_action = true; v = 0.0; }   // see clothb200_decode_actions_host
         double m = (hi[i] < v) ? hi[i] : v;
         a[i] = (lo[i] > m) ? lo[i] : m;
     }
@@ -332,10 +339,11 @@ __global__ void decode_actions_kernel(int n, const T *__restrict__ actions, Clot
     if (delta_actions) {
         const double stepl = sqrt(xr * xr + yr * yr);
         int ii = 0;
-        if (stepl > 0.0) { double cur = 0; for (;;) { cur += stepl; if (cur >= total) break; ii += 1; } }
+        if (stepl > 0.0) { double cur = 0; for (;;) { cur += stepl; if (cur >= total || ii >= CLOTHB200_MAX_ITERS_PULL) break; ii += 1; } }
         ip = ii;
     } else ip = (int)(iters_pull_max * length);
     ClothB200Plan pl; pl.gx = x; pl.gy = y; pl.dxr = xr; pl.dyr = yr; pl.iters_pull = ip; pl.reserved = 0;
+    if (nan_action) { pl.gx = 0.5; pl.gy = 0.5; pl.dxr = 0.0; pl.dyr = 0.0; pl.iters_pull = 0; pl.reserved = CLOTHB200_PLAN_BAD_ACTION; }
     plans[e] = pl;
 }
 
@@ -422,6 +430,7 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     P.sweep_thresh = sweep_threshold();
     P.relax_iters = hp.reserved0 > 1 ? hp.reserved0 : 1;
     P.force_grab = hp.force_grab ? 1 : 0;
+    P.reward_abs = hp.reward_type == CLOTHB200_REWARD_COVERAGE ? 1 : 0;
     return 0;
 }
 

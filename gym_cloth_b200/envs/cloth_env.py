@@ -7,8 +7,13 @@
 All arithmetic of the hot path (Cloth.update, Gripper, the substep loop, coverage/reward/terminal)
 runs in libclothb200.so; this file holds only what the reference also does in Python: config handling,
 random draws for resets and the gym-style bookkeeping.  Random numbers are drawn from
-np.random.RandomState streams in exactly the order the reference draws them, environment i using
-seed + i, so environment i replays the reference ClothEnv seeded with seed + i (bit-exactly in f64).
+np.random.RandomState streams in exactly the order the reference draws them, environment i seeded like
+the reference's `env.seed(seed + i)` (gym 0.12.1 seeding, gym_cloth_b200/seeding.py), so environment i replays the
+reference ClothEnv seeded with seed + i (bit-exactly in f64).  The reference also draws 3 + 224*224*3 values of
+per-episode domain randomisation from the same stream at the end of every reset (cloth_env.py:786-789), whatever the
+observation type: the single-env `ClothEnv` facade replays them (every episode matches), `BatchedClothEnv` does so
+only with dom_rand_draws=True (otherwise its FIRST episode per environment matches and later ones use their own,
+equally distributed, draws - 150 531 draws per reset and environment are not free at 65 536 environments).
 """
 import copy
 import pickle
@@ -18,6 +23,7 @@ import torch
 import yaml
 
 from .. import lib as _l
+from .. import seeding as _seeding
 from ..batched import BatchedCloth
 
 _REWARD_THRESHOLDS = {"coverage": 0.92, "coverage-delta": 0.92}   # cloth_env.py:42-50 (coverage types only)
@@ -83,8 +89,8 @@ class BatchedClothEnv(object):
         self.add_dom_rand = str(env.get("use_dom_rand", "False")).lower() == "true"
         self.reward_type = env["reward_type"]
         assert "coverage" in self.reward_type             # cloth_env.py:130
-        if self.reward_type != "coverage-delta":
-            raise NotImplementedError(self.reward_type)
+        if self.reward_type not in _REWARD_THRESHOLDS:
+            raise ValueError(self.reward_type)            # cloth_env.py:679
         if not (env["clip_act_space"] and env["delta_actions"]):
             raise NotImplementedError("reset actions need delta_actions (cloth_env.py:861-862)")
         self.init_type = cfg["init"]["type"]
@@ -120,11 +126,12 @@ class BatchedClothEnv(object):
 
     # ------------------------------------------------------------------ seeding
     def seed(self, seed=None):
-        """Environment i draws from np.random.RandomState(seed + env_offset + i) (cloth_env.py:332-341)."""
+        """Environment i draws from the generator `ClothEnv.seed(seed + env_offset + i)` creates in the reference
+        (cloth_env.py:332-341): gym 0.12.1's seeding.np_random, i.e. MT19937 keyed by the SHA-512 hash of the seed."""
         if seed is None:
-            seed = int(np.random.SeedSequence().entropy % (2 ** 31))
+            seed = _seeding.create_seed() % (2 ** 31)
         self._seed = int(seed)
-        self.rngs = [np.random.RandomState((self._seed + self.env_offset + i) % (2 ** 32)) for i in range(self.n_env)]
+        self.rngs = [_seeding.np_random(self._seed + self.env_offset + i)[0] for i in range(self.n_env)]
         return [seed]
 
     # ------------------------------------------------------------------ helpers
@@ -505,10 +512,11 @@ class ClothEnv(object):
         self.num_points = self._b.N
         self.action_space = self._b.action_space
         self.observation_space = self._b.observation_space
+        # cloth_env.py:120-124: the reference's {"pts": [Point], "springs": [Spring]} pickle (or the array dict earlier
+        # versions of this package wrote)
         self._start_state = None
         if start_state_path is not None:
-            with open(start_state_path, "rb") as fh:
-                self._start_state = pickle.load(fh)
+            self._start_state = self._read_start_state(start_state_path)
         self.cloth = _ClothFacade(self._b)
         self.gripper = _GripperFacade(self._b, self.cloth)
         self.num_steps = 0; self.num_sim_steps = 0; self.have_tear = False
@@ -534,14 +542,31 @@ class ClothEnv(object):
         self.num_steps = int(c.num_steps[0].item()); self.num_sim_steps = int(c.num_sim_steps[0].item())
         self.have_tear = bool(c.flags[0].item() & _l.FLAG_TEAR)
 
+    def _read_start_state(self, path):
+        from .. import state_io
+        try:
+            st = state_io.state_to_arrays(state_io.load_state(path), self._b.P.num_width_points)
+        except ValueError:
+            with open(path, "rb") as fh:
+                st = pickle.load(fh)
+            if not (isinstance(st, dict) and "pos" in st and "prev" in st):
+                raise
+        return st
+
     def reset(self):
         b = self._b
         if self._start_state is not None:
+            # cloth_env.py:736-741: Cloth(state=deepcopy(start_state)) - pts and springs as saved, no init actions
             st = self._start_state
-            b.rngs[0].rand()               # Cloth.__init__ still draws init_side (cloth.pyx:75)
+            b.init_side[0] = b.rngs[0].rand() > 0.5      # Cloth.__init__ still draws init_side (cloth.pyx:75)
             b.cloth.set_state(st["pos"], st["prev"], st.get("pinned"))
             if "rest" in st:
-                b.cloth.set_rest(st["rest"])
+                rest = np.nan_to_num(np.asarray(st["rest"], np.float64))
+                if rest.size == 6 * b.N:                 # slot order q*6+k (state_io)
+                    b.cloth.rest = torch.from_numpy(rest).to(b.device, b.torch_dtype); b.cloth.rest_env_stride = 0
+                    b.cloth.exact_rest = True
+                else:                                    # spring-list order
+                    b.cloth.set_rest(rest)
             b.cloth.num_steps.zero_(); b.cloth.num_sim_steps.zero_()
             b._measure_subset(np.arange(1))
             b.cloth.prev_coverage.copy_(b.cloth.coverage)
@@ -551,6 +576,8 @@ class ClothEnv(object):
         self.cloth._invalidate()
         if self._start_state is None:
             self.cloth._orig = b.orig_pos[0].cpu().numpy()
+        elif "orig" in self._start_state:
+            self.cloth._orig = np.array(self._start_state["orig"], np.float64)     # Point.orig_* travel with the pickle
         elif self.cloth._orig is None:
             self.cloth._orig = self.cloth.allpts_arr
         self._sync_counters()
@@ -592,10 +619,27 @@ class ClothEnv(object):
         return self._b.get_random_action(atype)[0]
 
     def save_state(self, cloth_file):
-        """Like cloth_env.py:343-350, but arrays instead of pickled Point objects."""
-        pos, prev, pin, _ = self._b.cloth.get_state(0)
-        with open(cloth_file, "wb") as fh:
-            pickle.dump({"pos": pos, "prev": prev, "pinned": pin}, fh)
+        """cloth_env.py:343-350: pickle {"pts": cloth.pts, "springs": cloth.springs} - the reference's own object graph
+        (gym_cloth_b200/state_io.py), loadable by the reference's ClothEnv(start_state_path=...) and by this one."""
+        from .. import state_io
+        b = self._b
+        pos, prev, pin, _ = b.cloth.get_state(0)
+        orig = self.cloth._orig if self.cloth._orig is not None else pos
+        state_io.save_state(cloth_file, pos, prev, pin, orig, self._rest_slots(), b.P.num_width_points, self.bounds)
+
+    def _rest_slots(self):
+        """Spring.rest_length of environment 0 in slot order q*6+k (double)."""
+        import ctypes as C
+        c = self._b.cloth
+        if c.rest is not None:
+            r = c.rest if c.rest_env_stride == 0 else c.rest[0]
+            return r.double().cpu().numpy()
+        # f32 tier-1/3 batches keep no table: the construction-time lengths of the flat grid (cloth.pyx:417), in double
+        N = self._b.N
+        pos4 = np.zeros((N, 4)); prev4 = np.zeros((N, 4)); rest6 = np.zeros(6 * N)
+        _l.check(_l.lib().clothb200_init_grid_f64(C.byref(self._b.P), 1, None, 1, pos4.ctypes.data, prev4.ctypes.data,
+                                                  rest6.ctypes.data), "init_grid")
+        return rest6
 
     def render(self, filepath, mode="human", close=False):
         pass   # the OpenGL viewer is a display-only side channel (SURVEY.md §2 row 12)

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libclothb200.so")
 OK = 0
 FLAG_TEAR, FLAG_OOB, FLAG_NOGRAB, FLAG_BADSTATE = 1, 2, 4, 8
 MODE_REFERENCE_ORDER, MODE_COLOURED = 0, 1
+REWARD_TYPE = {"coverage-delta": 0, "coverage": 1}
 INIT_TIER = {"tier1": 1, "tier2": 2, "tier3": 3}
 
 
@@ -34,6 +35,7 @@ class Params(C.Structure):
         ("reduce_factor", C.c_double), ("grip_radius", C.c_double), ("gripper_height", C.c_double),
         ("clip_act_space", C.c_int32), ("delta_actions", C.c_int32),
         ("force_grab", C.c_int32), ("reserved0", C.c_int32),
+        ("reward_type", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -198,6 +200,11 @@ def params_from_cfg(cfg):
     P.gripper_height = cl["height"]                      # Gripper(cloth, grip_radius, cfg.cloth.height, ...) cloth_env.py:752
     P.clip_act_space = int(bool(env["clip_act_space"])); P.delta_actions = int(bool(env["delta_actions"]))
     P.force_grab = int(bool(env.get("force_grab", False)))
+    rt = env.get("reward_type", "coverage-delta")
+    assert "coverage" in rt                              # cloth_env.py:130
+    if rt not in REWARD_TYPE:
+        raise ValueError(rt)                             # cloth_env.py:679 (the height/variance types fail the assert above)
+    P.reward_type = REWARD_TYPE[rt]
     check(lib().clothb200_params_validate(C.byref(P)), "params_validate")
     return P
 

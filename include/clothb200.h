@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CLOTHB200_VERSION 100 /* 0.1.0 */
+#define CLOTHB200_VERSION 110 /* 0.1.1: ClothB200Params.reward_type */
 
 /* error codes */
 #define CLOTHB200_OK 0
@@ -54,6 +54,10 @@ extern "C" {
 /* relaxation ordering */
 #define CLOTHB200_MODE_REFERENCE_ORDER 0 /* replays the Cython Gauss-Seidel order exactly */
 #define CLOTHB200_MODE_COLOURED 1        /* graph-coloured parallel Gauss-Seidel (not bit-comparable) */
+
+/* cfg env.reward_type: the two types the reference admits (`assert 'coverage' in self.reward_type`, cloth_env.py:130) */
+#define CLOTHB200_REWARD_COVERAGE_DELTA 0 /* rew += coverage - previous coverage (cloth_env.py:660-662) */
+#define CLOTHB200_REWARD_COVERAGE 1       /* rew += coverage (cloth_env.py:657-659) */
 
 /* initial grid types (cfg init.type, cloth.pyx:94-132) */
 #define CLOTHB200_INIT_TIER1 1
@@ -74,6 +78,8 @@ typedef struct ClothB200Params {
     int32_t clip_act_space, delta_actions;
     int32_t force_grab;
     int32_t reserved0;                           /* coloured mode: limit passes per update (relax_iters); 0/1 = one pass */
+    int32_t reward_type;                         /* cfg env.reward_type (cloth_env.py:657-662): CLOTHB200_REWARD_* */
+    int32_t reserved1;
 } ClothB200Params;
 
 /* One decoded pull action (cloth_env.py:401-470): where to grip, the per-substep pull delta and
@@ -82,8 +88,12 @@ typedef struct ClothB200Plan {
     double gx, gy;      /* grip point passed to Gripper.grab_top (cloth_env.py:431) */
     double dxr, dyr;    /* x_dir_r, y_dir_r (cloth_env.py:455-456) */
     int32_t iters_pull; /* cloth_env.py:460-470 */
-    int32_t reserved;
+    int32_t reserved;   /* bit 0 = CLOTHB200_PLAN_BAD_ACTION: the action held a NaN.  The reference's iters_pull loop
+                           (cloth_env.py:462-467) never exits on one; here the step grips nothing, runs no substep and
+                           sets CLOTHB200_FLAG_BADSTATE | CLOTHB200_FLAG_NOGRAB. */
 } ClothB200Plan;
+#define CLOTHB200_PLAN_BAD_ACTION 1
+#define CLOTHB200_MAX_ITERS_PULL (1 << 24) /* bound of the iters_pull accumulation loop (degenerate reduce_factor) */
 
 /* All per-environment tensors one step touches.  DEVICE pointers.  Optional ones may be NULL. */
 typedef struct ClothB200Step {

@@ -57,24 +57,50 @@ if __name__ == "__main__":
             q = lambda x: " ".join("%.2e" % v for v in np.percentile(x, [50, 90, 99, 100]))
             print("action %d: max|d| p50/90/99/100: %s | mean|d|: %s | dcov: %s | same substeps %.3f same ngrab %.3f | cov mean f32 %.4f f64 %.4f" % (
                 step, q(mx), q(mn), q(dc), same, sameg, a32.coverage.mean().item(), a64.coverage.mean().item()))
-    elif what == "phases":
+    elif what in ("phases", "benchphases"):
         import ctypes as C
         dt = torch.float32 if (len(sys.argv) < 4 or sys.argv[3] == "f32") else torch.float64
         rng = np.random.RandomState(0)
-        bc = BatchedCloth(L.default_params(), n, dtype=dt, mode=int(os.environ.get("MODE", "0")))
-        a0 = torch.from_numpy(actions(rng, n)).to("cuda", dt)
-        bc.step_actions(a0); torch.cuda.synchronize()
+        if what == "phases":
+            bc = BatchedCloth(L.default_params(), n, dtype=dt, mode=int(os.environ.get("MODE", "0")))
+            a0 = torch.from_numpy(actions(rng, n)).to("cuda", dt)
+            bc.step_actions(a0); torch.cuda.synchronize()
+            a = torch.from_numpy(actions(rng, n)).to("cuda", dt)
+            step = lambda: bc.step_actions(a)
+        else:
+            # the contract bench's workload (bench.py): tier-1 reset pool, warm-up steps with restarts, then one profiled step
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            import bench as B
+            from gym_cloth_b200 import cfg_path
+            from gym_cloth_b200.envs import BatchedClothEnv
+            env = BatchedClothEnv(cfg_path(1), n, dtype="f32" if dt == torch.float32 else "f64", seed=1337)
+            env.reset(); pool = env.snapshot(); bc = env.cloth
+            for t in range(3):
+                env.step(torch.from_numpy(B.actions_for_step(1337, t, 0, n)).to("cuda", dt))
+                done = torch.nonzero(bc.done)[:, 0]
+                if done.numel():
+                    g = np.random.Generator(np.random.Philox(key=1338, counter=[t, 0, 0, 0]))
+                    env.reset_from_pool(pool, done, torch.from_numpy(g.integers(0, n, size=int(done.numel()))).to("cuda"))
+            a = torch.from_numpy(B.actions_for_step(1337, 3, 0, n)).to("cuda", dt)
+            step = lambda: env.step(a)
+            torch.cuda.synchronize()
+        if os.environ.get("NCU"):
+            # ncu --profile-from-start off ... : capture exactly this launch, without the cycle counters
+            torch.cuda.profiler.start(); step(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+            print("substeps", int(bc.sim_steps.sum().item()))
+            sys.exit(0)
         prof = torch.zeros(n, 16, dtype=torch.int64, device="cuda")
         L.lib().clothb200_debug_set_profile(C.c_void_p(prof.data_ptr()))
-        a = torch.from_numpy(actions(rng, n)).to("cuda", dt)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); bc.step_actions(a); e1.record(); torch.cuda.synchronize()
+        e0.record(); step(); e1.record(); torch.cuda.synchronize()
         L.lib().clothb200_debug_set_profile(None)
         p = prof.cpu().numpy().astype(np.float64)
         act = p[:, 10] > 0
-        names = ["hooke_verlet", "commit_hash", "alloc", "scatter", "order+snap", "(unused)", "coll_first_plane", "coll_replay", "limit_snap", "limit_replay"]
-        tot = p[act, :10].sum()
+        names = ["hooke_verlet", "commit_hash", "alloc", "scatter", "(coll: grab, 4 warps)", "(unused)", "(coll: work, 4 warps)", "collide_buckets", "limit_snap", "limit_resolve"]
         nsub = p[act, 10].sum()
+        print("  collide_buckets per warp: taking work %.0f cyc/substep, working %.0f cyc/substep (sums over the 4 warps / 4)" % (p[act, 4].sum() / nsub / 4, p[act, 6].sum() / nsub / 4))
+        p[:, 4] = 0; p[:, 6] = 0
+        tot = p[act, :10].sum()
         print("%s: %.1f ms; active envs %d; substeps %d; cycles/substep/CTA %.0f" % (str(dt), e0.elapsed_time(e1), act.sum(), nsub, tot / nsub))
         for i, nm in enumerate(names):
             print("  %-18s %6.1f %%  %9.0f cyc/substep" % (nm, 100 * p[act, i].sum() / tot, p[act, i].sum() / nsub))

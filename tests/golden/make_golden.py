@@ -18,6 +18,8 @@ Fixtures (float64 unless noted; N=625):
   tear.npz             an action that tears the cloth (loop break, sticky flag)
   env_t{1,2,3}_s*.npz  reset() + K step(action) through the reference ClothEnv: states, reward,
                        done, info, grabbed index lists, iters_pull, and the np_random draw log
+  state_t1_s1337.pkl   the file the reference's ClothEnv.save_state wrote ({"pts": [Point], "springs": [Spring]})
+  state_t1_s1337.npz   that state as arrays + reset()/step() of a second reference env started from the file
 """
 import argparse
 import json
@@ -287,6 +289,48 @@ def gen_policy(out, tier=1, seed=1337, episodes=2, kind="oracle", max_t=None):
     np.savez_compressed(os.path.join(out, "policy_%s_t%d_s%d.npz" % (kind, tier, seed)), **d)
 
 
+def gen_state(out, tier=1, seed=1337):
+    """save_state / start_state_path (cloth_env.py:343-350, 120-124, 736-741): the reference env pickles its
+    {"pts", "springs"} after one action; a second reference env starts from that file, resets and steps."""
+    import pickle
+    tmp = tempfile.mkdtemp(prefix="golden_state_")
+    env = _make_env(tier, seed, tmp)
+    env.reset()
+    rng = np.random.RandomState(seed + 17)
+    pt = env.cloth.pts[int(rng.randint(len(env.cloth.pts)))]
+    a1 = (float((pt.x - 0.5) * 2), float((pt.y - 0.5) * 2), 0.31, -0.22)
+    env.step(a1)
+    pkl = os.path.join(out, "state_t%d_s%d.pkl" % (tier, seed))
+    env.save_state(pkl)
+    d = {"tier": tier, "seed": seed}
+    d["pos_saved"], d["prev_saved"], d["pin_saved"] = _state(env.cloth)
+    d["orig_saved"] = np.array([[p.orig_x, p.orig_y, p.orig_z] for p in env.cloth.pts])
+    d["rest_saved"] = np.array([sp.rest_length for sp in env.cloth.springs])
+    # a fresh reference env started from the file
+    from oracle.ref_loader import load_env
+    ClothEnv = load_env(REFERENCE)
+    env2 = ClothEnv(os.path.join(tmp, "t%d.yaml" % tier), start_state_path=pkl)
+    env2.seed(seed + 1)
+    env2._wd = env2._hd = 224
+    obs0 = env2.reset()
+    d["pos_reset"], d["prev_reset"], d["pin_reset"] = _state(env2.cloth)
+    d["obs_reset"] = np.asarray(obs0); d["start_coverage"] = env2._start_coverage
+    d["init_side"] = bool(env2.cloth.init_side)
+    pt = env2.cloth.pts[int(rng.randint(len(env2.cloth.pts)))]
+    a2 = (float((pt.x - 0.5) * 2), float((pt.y - 0.5) * 2), -0.28, 0.35)
+    obs, rew, done, info = env2.step(a2)
+    d["action"] = np.array(a2); d["reward"] = rew; d["done"] = done
+    d["info"] = np.array([info["num_steps"], info["num_sim_steps"], info["actual_coverage"], info["variance_inv"],
+                          float(info["have_tear"]), float(info["out_of_bounds"])])
+    d["pos_a0"], d["prev_a0"], d["pin_a0"] = _state(env2.cloth)
+    # second episode from the same file: the reference deep-copies the start state at every reset
+    obs1 = env2.reset()
+    d["pos_reset2"], _, _ = _state(env2.cloth)
+    np.savez_compressed(os.path.join(out, "state_t%d_s%d.npz" % (tier, seed)), **d)
+    print("state: saved %s (%d bytes), step from it: rew %.4f cov %.4f sim %d" % (
+        pkl, os.path.getsize(pkl), rew, info["actual_coverage"], info["num_sim_steps"]))
+
+
 def gen_decode(out):
     """Action decode exactly as ClothEnv.step computes it (cloth_env.py:401-475), captured by
     hooking gripper.grab_top and _pull with the physics update stubbed out."""
@@ -372,7 +416,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "state"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -387,14 +431,14 @@ def main():
                 ["env", "--tier", "1", "--seed", "1338", "--actions", "3"],
                 ["env", "--tier", "2", "--seed", "1337", "--actions", "2"],
                 ["env", "--tier", "3", "--seed", "1337", "--actions", "2"], ["policy"],
-                ["policy_highest", "--tier", "3", "--seed", "1337"]]
+                ["policy_highest", "--tier", "3", "--seed", "1337"], ["state"]]
         procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__)] + j + ["--out", a.out]) for j in jobs]
         rc = [p.wait() for p in procs]
         print("exit codes", rc)
         sys.exit(max(rc))
     if a.what == "policy_highest":
         return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="highest", max_t=3)
-    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy}.get(
+    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy, "state": gen_state}.get(
         a.what, lambda out: gen_env(out, a.tier, a.seed, a.actions))(a.out)
 
 
