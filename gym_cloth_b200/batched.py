@@ -21,10 +21,10 @@ class BatchedCloth(object):
     gripper.pyx) for `n_env` independent environments on one GPU."""
 
     def __init__(self, params, n_env, dtype=torch.float32, device=None, init_type="tier1", noise=None,
-                 init_side=True, exact_rest=None, mode=_l.MODE_REFERENCE_ORDER):
+                 init_side=True, exact_rest=None, mode=_l.MODE_REFERENCE_ORDER, variant=None):
         if not torch.cuda.is_available():
             raise _l.ClothB200Error("BatchedCloth needs a CUDA device (no CPU fallback)")
-        self.L = _l.lib()
+        self.L = _l.lib(variant)
         self.P = params
         self.n_env = int(n_env)
         self.dtype = dtype

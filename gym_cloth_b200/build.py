@@ -41,15 +41,40 @@ def _newest_src():
     return t
 
 
+LIB_IEEE = os.path.join(HERE, "libclothb200_f32ieee.so")
+# study variant of the f32 build: the reference's expressions in float (sqrt and division as written, no rsqrt forms),
+# IEEE-rounded div/sqrt, denormals kept, FMA contraction as in production.  Only the f32 entry points are meaningful.
+IEEE = ["-DCLOTHB200_F32_REFERENCE_FORMS", "-ftz=false", "-prec-div=true", "-prec-sqrt=true"]
+UNITS_IEEE = [("cloth_f32.cu", "ieee_cloth_f32.o", IEEE), ("cloth_f64.cu", "cloth_f64.o", None), ("cloth_abi.cu", "cloth_abi.o", None)]
+for _w in (25, 0, 64):
+    UNITS_IEEE.append(("cloth_inst.cu", "ieee_cloth_inst_f32_w%d.o" % _w, IEEE + ["-DCLOTH_T=float", "-DCLOTH_INSTANTIATE_WC=%d" % _w]))
+    UNITS_IEEE.append(("cloth_inst.cu", "cloth_inst_f64_w%d.o" % _w, None))
+
+
+def build_ieee(force=False, verbose=False):
+    """libclothb200_f32ieee.so (needs the objects of the main build for the shared f64 / ABI units)."""
+    build(force=False, verbose=verbose)
+    if not force and os.path.exists(LIB_IEEE) and os.path.getmtime(LIB_IEEE) >= _newest_src():
+        return LIB_IEEE
+    return _build(LIB_IEEE, [u for u in UNITS_IEEE], verbose)
+
+
 def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_src():
         return LIB
+    return _build(LIB, UNITS, verbose)
+
+
+def _build(LIB, UNITS, verbose):
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
     procs = []
     objs = []
     for src, oname, extra in UNITS:
         obj = os.path.join(OBJ, oname)
+        if extra is None:            # reuse the object of the main build
+            objs.append(obj)
+            continue
         objs.append(obj)
         cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,3 +91,5 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--ieee" in sys.argv:
+        print(build_ieee(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -200,7 +200,14 @@ template <typename A_t> __device__ __forceinline__ int queue_head_remaining(cons
 template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> struct ClothCTA {
     typedef typename V4<T>::type P4;
     static constexpr int NWARPS = NT / 32;
-    static constexpr bool FAST = (sizeof(T) == 4);   // f32 production math; the f64 build evaluates the reference's expressions
+    // f32 production math (rsqrt / squared-distance forms of the reference's expressions); the f64 build evaluates the
+    // reference's expressions themselves.  CLOTHB200_F32_REFERENCE_FORMS builds the float kernels that way too (study
+    // variant libclothb200_f32ieee.so: IEEE div/sqrt, no flush-to-zero - gym_cloth_b200/build.py, scripts/f32_drift.py).
+#ifdef CLOTHB200_F32_REFERENCE_FORMS
+    static constexpr bool FAST = false;
+#else
+    static constexpr bool FAST = (sizeof(T) == 4);
+#endif
 
     const DevParams<T> &P;
     const int W, H, N;
@@ -705,7 +712,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             if (k == 0) {
                 // a pile of more than 32 points: members in 2 or 4 registers per lane, or the shared-memory path
                 const int cnt = __shfl_sync(FULL, cnt_i, 0), start = __shfl_sync(FULL, start_i, 0);
-                if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)cnt); atomicAdd((unsigned long long *)&pacc[5], 1ull); }
+                if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)cnt * (unsigned long long)(cnt - 1)); atomicAdd((unsigned long long *)&pacc[5], 1ull); }
                 if (!ORDERED) order_bucket(start, cnt);
                 if (cnt <= 64) replay_bucket_regs<2>(lst, start, cnt, 0);
                 else if (cnt <= 128) replay_bucket_regs<4>(lst, start, cnt, 0);
@@ -722,7 +729,13 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             const bool valid = lane < total;
             const int seg_cnt = valid ? s_cnt : 0, seg_base = valid ? s_end - s_cnt : 0, li = lane - seg_base;
             const int maxcnt = __reduce_max_sync(FULL, seg_cnt);
-            if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[14], (unsigned long long)total); atomicAdd((unsigned long long *)&pacc[11], (unsigned long long)k); }
+            if (prof_on) {   // members, buckets and ordered pair tests n(n-1) of this group (SURVEY.md 8d's P)
+                const int pairs = __reduce_add_sync(FULL, valid ? seg_cnt - 1 : 0);
+                if (lane == 0) {
+                    atomicAdd((unsigned long long *)&pacc[14], (unsigned long long)total); atomicAdd((unsigned long long *)&pacc[11], (unsigned long long)k);
+                    atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)pairs);
+                }
+            }
             int mine = valid ? lstA[s_start + li] : 0;
             if (!ORDERED) {
                 // members into point-index order: rank inside the segment, permute through the bucket's lstB range

@@ -132,16 +132,24 @@ def exported_symbols():
 
 
 _lib = None
+_variants = {}
+LIB_IEEE_PATH = os.path.join(HERE, "libclothb200_f32ieee.so")
 
 
-def lib():
+def lib(variant=None):
+    """The shared library.  variant='f32ieee': the study build of the f32 kernels (reference expressions, IEEE div/sqrt,
+    no flush-to-zero; `python -m gym_cloth_b200.build --ieee`) - loaded side by side, used by scripts/f32_drift.py and
+    the drift test only."""
     global _lib
-    if _lib is not None:
+    if variant is None and _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if variant is not None and variant in _variants:
+        return _variants[variant]
+    path = LIB_PATH if variant is None else {"f32ieee": LIB_IEEE_PATH}[variant]
+    if not os.path.exists(path):
         raise ClothB200Error(
-            "libclothb200.so is not built (%s). Run `python -m gym_cloth_b200.build`; there is no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+            "%s is not built. Run `python -m gym_cloth_b200.build%s`; there is no CPU fallback." % (path, "" if variant is None else " --ieee"))
+    L = C.CDLL(path)
     for name, (res, args) in _PROTOS.items():
         f = getattr(L, name); f.restype = res; f.argtypes = args
     for base, (res, args) in _TYPED.items():
@@ -151,7 +159,10 @@ def lib():
     assert L.clothb200_sizeof_plan() == C.sizeof(Plan), "Plan layout mismatch"
     assert L.clothb200_sizeof_step() == C.sizeof(Step), "Step layout mismatch"
     assert L.clothb200_sizeof_scene() == C.sizeof(Scene), "Scene layout mismatch"
-    _lib = L
+    if variant is None:
+        _lib = L
+    else:
+        _variants[variant] = L
     return L
 
 

@@ -87,6 +87,12 @@ def ref_coverage(c):
         return 0
 
 
+def _oob(pos):
+    """ClothEnv._out_of_bounds (cloth_env.py:1020-1045): bounds (1,1,1), slack 0.25."""
+    x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+    return bool(((x >= 1.25) | (x < -0.25) | (y >= 1.25) | (y < -0.25) | (z >= 1) | (z < 0)).any())
+
+
 def _worker(args):
     kind, pos, prev, action = args
     t0 = time.perf_counter()
@@ -94,19 +100,26 @@ def _worker(args):
         c, g = make_ref_cloth(pos, prev)
         n = ref_step(c, g, action)
         cov = ref_coverage(c)
+        t1 = time.perf_counter()
+        new_pos = np.array([[p.x, p.y, p.z] for p in c.pts]); new_prev = np.array([[p.px, p.py, p.pz] for p in c.pts])
+        tear = bool(c.cloth_have_tear)
     else:
         from oracle.oracle import OracleCloth
         o = OracleCloth()
         o.set_state(pos, prev, np.zeros(len(pos), np.uint8))
         n, _, _ = o.step_action(np.asarray(action, np.float64))
         cov = o.coverage()
-    return n, cov, time.perf_counter() - t0
+        t1 = time.perf_counter()
+        st = o.get_state()
+        new_pos, new_prev = st[0], st[1]
+        tear = bool(o.tear)
+    return n, cov, t1 - t0, new_pos, new_prev, tear, _oob(new_pos)
 
 
 def cpu_env_steps(kind, states, actions, cores=None):
     """Run len(actions) env.step calls on `cores` host processes (one ClothEnv each, like the reference's
     'one CPU per analytic.py process' model, analysis/README.md:9-11).  states: list of (pos, prev).
-    Returns dict(value env-steps/s, substeps/s, seconds, cores, n)."""
+    Returns dict(value env-steps/s, substeps/s, seconds, cores, n, and per call: coverage, the new (pos, prev), tear, oob)."""
     cores = cores or os.cpu_count() or 1
     jobs = [(kind, s[0], s[1], a) for s, a in zip(states, actions)]
     cores = max(1, min(cores, len(jobs)))
@@ -120,4 +133,5 @@ def cpu_env_steps(kind, states, actions, cores=None):
     dt = time.perf_counter() - t0
     sub = sum(r[0] for r in res)
     return {"value": len(jobs) / dt, "substeps_per_s": sub / dt, "seconds": dt, "cores": cores, "n": len(jobs),
-            "substeps": sub, "coverage": [r[1] for r in res]}
+            "substeps": sub, "coverage": [r[1] for r in res], "states": [(r[3], r[4]) for r in res],
+            "tear": [r[5] for r in res], "oob": [r[6] for r in res], "n_updates": [r[0] for r in res]}

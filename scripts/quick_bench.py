@@ -104,7 +104,7 @@ if __name__ == "__main__":
         print("%s: %.1f ms; active envs %d; substeps %d; cycles/substep/CTA %.0f" % (str(dt), e0.elapsed_time(e1), act.sum(), nsub, tot / nsub))
         for i, nm in enumerate(names):
             print("  %-18s %6.1f %%  %9.0f cyc/substep" % (nm, 100 * p[act, i].sum() / tot, p[act, i].sum() / nsub))
-        print("  replayed members/substep: small buckets %.1f, big (>32) buckets %.1f; big buckets/substep %.2f" % (p[act, 14].sum() / nsub, p[act, 15].sum() / nsub, p[act, 5].sum() / nsub))
+        print("  members of <=32-point buckets/substep %.1f; ordered pair tests P/substep %.0f (flat cloth: 4704); >32-point buckets/substep %.2f" % (p[act, 14].sum() / nsub, p[act, 15].sum() / nsub, p[act, 5].sum() / nsub))
         print("  replay buckets/substep %.2f  limit pops/substep %.2f  shortened/substep %.2f" % (p[act, 11].sum() / nsub, p[act, 12].sum() / nsub, p[act, 13].sum() / nsub))
         per = p[act, :10].sum(1) / p[act, 10]
         print("  per-env cycles/substep percentiles 10/50/90/100:", np.percentile(per, [10, 50, 90, 100]).round(0))

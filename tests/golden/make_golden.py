@@ -18,6 +18,8 @@ Fixtures (float64 unless noted; N=625):
   tear.npz             an action that tears the cloth (loop break, sticky flag)
   env_t{1,2,3}_s*.npz  reset() + K step(action) through the reference ClothEnv: states, reward,
                        done, info, grabbed index lists, iters_pull, and the np_random draw log
+  bench_pool_t1.npz    64 tier-1 reset states (env seeds 1337..1400) from the reference's own reset(): start states of
+                       bench.py's reference arm / cpu_baseline (not part of `all`: ~5 min)
   state_t1_s1337.pkl   the file the reference's ClothEnv.save_state wrote ({"pts": [Point], "springs": [Spring]})
   state_t1_s1337.npz   that state as arrays + reset()/step() of a second reference env started from the file
 """
@@ -331,6 +333,28 @@ def gen_state(out, tier=1, seed=1337):
         pkl, os.path.getsize(pkl), rew, info["actual_coverage"], info["num_sim_steps"]))
 
 
+def _bench_pool_one(args):
+    seed, tmpdir = args
+    env = _make_env(1, seed, tempfile.mkdtemp(prefix="golden_pool_", dir=tmpdir))
+    env.reset()
+    pos, prev, _ = _state(env.cloth)
+    return seed, pos, prev, env._start_coverage
+
+
+def gen_bench_pool(out, base_seed=1337, n=64):
+    """Start states of bench.py's reference arm: the reference's own tier-1 reset() (cloth_env.py:717-891) for env seeds
+    base_seed .. base_seed+n-1 - the seeds of the first n environments of the GPU arm, whose f64 reset is bit-equal."""
+    import multiprocessing as mp
+    tmp = tempfile.mkdtemp(prefix="golden_pool_")
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_bench_pool_one, [(base_seed + i, tmp) for i in range(n)], chunksize=1)
+    res.sort()
+    np.savez_compressed(os.path.join(out, "bench_pool_t1.npz"), seeds=np.array([r[0] for r in res]),
+                        pos=np.stack([r[1] for r in res]), prev=np.stack([r[2] for r in res]),
+                        start_coverage=np.array([r[3] for r in res]))
+    print("bench pool: %d tier-1 reset states, mean start coverage %.4f" % (n, np.mean([r[3] for r in res])))
+
+
 def gen_decode(out):
     """Action decode exactly as ClothEnv.step computes it (cloth_env.py:401-475), captured by
     hooking gripper.grab_top and _pull with the physics update stubbed out."""
@@ -416,7 +440,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "state"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "state", "bench_pool"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -438,7 +462,7 @@ def main():
         sys.exit(max(rc))
     if a.what == "policy_highest":
         return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="highest", max_t=3)
-    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy, "state": gen_state}.get(
+    {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy, "state": gen_state, "bench_pool": gen_bench_pool}.get(
         a.what, lambda out: gen_env(out, a.tier, a.seed, a.actions))(a.out)
 
 

@@ -34,7 +34,7 @@ def test_exports_every_declared_symbol(so):
 
 
 def test_struct_layouts_and_defaults(so):
-    assert so.clothb200_version() == 100
+    assert so.clothb200_version() == 110
     P = L.default_params()
     assert (P.num_width_points, P.ks, P.iters_rest, P.grip_radius, P.max_actions) == (25, 10000.0, 1000.0, 0.003, 10)
     assert so.clothb200_error_string(-1).startswith(b"bad argument")

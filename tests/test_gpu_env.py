@@ -108,7 +108,8 @@ def test_reward_type_coverage():
     """cfg env.reward_type 'coverage' (cloth_env.py:657-659): the reward is the coverage itself (+ the same bonuses and
     penalties), 'coverage-delta' (:660-662) its change; states and termination are the same."""
     from gym_cloth_b200 import cfg_path
-    from gym_cloth_b200.envs import BatchedClothEnv, load_cfg
+    from gym_cloth_b200.envs import BatchedClothEnv
+    from gym_cloth_b200.envs.cloth_env import load_cfg
     cfg = load_cfg(cfg_path(1))
     acts = np.array([[0.1, 0.2, 0.3, -0.2], [-0.4, 0.3, -0.2, 0.25], [0.99, 0.99, 0.1, 0.1]])
     out = {}
