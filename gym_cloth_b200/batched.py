@@ -70,7 +70,15 @@ class BatchedCloth(object):
         return np.float32 if self.dtype == torch.float32 else np.float64
 
     def _f(self, base):
-        return getattr(self.L, base + self.sfx)
+        """The typed entry point, called with this batch's device current (launches, attribute caches and scratch
+        buffers of the library all belong to the current device)."""
+        fn = getattr(self.L, base + self.sfx)
+        dev = self.device
+
+        def call(*args):
+            with torch.cuda.device(dev):
+                return fn(*args)
+        return call
 
     def io(self, measure=True, bookkeeping=True, obs=True, grab_mask=True):
         s = _l.Step()

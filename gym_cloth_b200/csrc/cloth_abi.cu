@@ -156,9 +156,12 @@ static double clampd(double v, double lo, double hi) {
 // per-thread scratch of the *_host entry points
 struct HostScratch {
     ClothB200Plan *pinned = nullptr, *dev = nullptr;
-    int cap = 0;
+    int cap = 0, device = -1;
     int ensure(int n) {
-        if (n <= cap) return CLOTHB200_OK;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (n <= cap && cur == device) return CLOTHB200_OK;      // the device buffer belongs to the device it was made on
+        device = cur;
         if (pinned) cudaFreeHost(pinned);
         if (dev) cudaFree(dev);
         pinned = nullptr; dev = nullptr; cap = 0;

@@ -311,8 +311,14 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         const T q = d0 * d0 + d1 * d1 + d2 * d2;
         T fm;
         if (FAST) {
-            fm = kk - (kk * rst) * rsqrtf((float)q);          // ks*kc*(l-rest)/l
-        } else {
+            // ks*kc*(l-rest)/l; a spring that does not exist gets coefficient 0, a zero-length one gives inf -> NaN
+            // positions, which commit_and_hash() reports as BADSTATE (the reference raises ZeroDivisionError here)
+            fm = valid ? kk - (kk * rst) * rsqrtf((float)q) : T(0);
+            if (SIGN > 0) { fx += fm * d0; fy += fm * d1; fz += fm * d2; }
+            else { fx -= fm * d0; fy -= fm * d1; fz -= fm * d2; }
+            return;
+        }
+        {
             const T l = sqrt_t(q);                               // fastnorm
             fm = kk * (l - rst) / l;
         }
@@ -497,7 +503,8 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         for (int k = 0; k < K; k++) {
             const int m = k * 32 + lane;
             mine[k] = m < cnt ? lstB[start + m] : 0;
-            Pm[k] = pos[mine[k]];
+            Pm[k] = mk4(T(0), T(0), T(0), T(1));
+            if (m < cnt) Pm[k] = pos[mine[k]];
             dirty[k] = false;
         }
 #pragma unroll
@@ -575,13 +582,31 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // looked at.  Cells are small (9 points on a flat cloth), so consecutive cells of the work list are packed side
     // by side into the 32 lanes ("segments") and advance in lock step.  No snapshot pre-test, no per-point gather.
     // ==================================================================================================
-    // The work list is kept sorted by bucket size, largest first (a counting sort over the size classes 2..32 and
-    // "more than 32"): lock-stepped segments then have similar lengths, and the piles, which take longest, start first.
-    // Class counters live at the head of lstB, which is idle until collide_buckets(); hooke_verlet() zeroes them.
-    // The list itself: behind the counters (ordered scatter: lstB has no other use) or in the key area (dead after pass 1).
-    static constexpr int NCLS = 34;                                  // class = min(cnt, 33); 0 and 1 unused
+    // The work list is kept sorted by SLOT class, largest first: a bucket of n members is given a slot of SLOT >= n
+    // lanes (n > 32: a "pile", its own path), and 32 / SLOT buckets of one class sit side by side in a warp, so a group
+    // of the work list is just (class, i-th group of the class) - nothing is packed, scanned or negotiated at run time:
+    //     class        0     1      2      3     4   5   6   7   8   9   10
+    //     members    > 32  17-32  11-16  9-10    8   7   6   5   4   3    2
+    //     SLOT         -    32     16     10     8   7   6   5   4   3    2
+    //     per group    1     1      2      3     4   4   5   6   8  10   16
+    // Class counters, fill counters and the per-class offsets live at the head of lstB, which is idle until
+    // collide_buckets(); hooke_verlet() zeroes them.  The list itself: behind them (ordered scatter: lstB has no other
+    // use) or in the key area (dead after pass 1).
+    static constexpr int NCLS = 34;                                  // ints reserved per counter block
+    static constexpr int NSC = 11;                                   // slot classes
+    __device__ __forceinline__ static int cls_of(uint32_t cnt) {
+        return cnt > 32u ? 0 : (cnt > 16u ? 1 : (cnt > 10u ? 2 : (cnt > 8u ? 3 : 12 - (int)cnt)));
+    }
+    __device__ __forceinline__ static int pack8(unsigned long long lo, unsigned long long hi, int c) {
+        return (int)(((c < 8 ? lo >> (8 * c) : hi >> (8 * (c - 8)))) & 255ull);
+    }
+    __device__ __forceinline__ static int cls_slot(int c) { return pack8(0x050607080a102040ull, 0x020304ull, c); }
+    __device__ __forceinline__ static int cls_cap(int c) { return pack8(0x0605040403020101ull, 0x100a08ull, c); }
+    __device__ __forceinline__ static int cls_mul(int c) { return pack8(0x342b25201a100804ull, 0x805640ull, c); }   // ceil(256 / SLOT): lane / SLOT = lane * mul >> 8
     __device__ __forceinline__ int *size_count() const { return reinterpret_cast<int *>(lstB); }
     __device__ __forceinline__ int *size_fill() const { return reinterpret_cast<int *>(lstB) + NCLS; }
+    __device__ __forceinline__ int *group_off() const { return size_fill() + NSC; }       // first group of each class
+    __device__ __forceinline__ int *item_off() const { return size_fill() + 2 * NSC; }    // first work-list index of each class
     __device__ __forceinline__ uint16_t *worklist() const { return ORDERED ? lstB + 4 * NCLS : reinterpret_cast<uint16_t *>(tkey); }
     // member list of the buckets in point-index order
     __device__ __forceinline__ const uint16_t *ordered_list() const { return ORDERED ? lstA : lstB; }
@@ -591,7 +616,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         if (ORDERED) { cnt = (int)(info & 1023u); start = (int)((info >> 10) & 1023u); }
         else { cnt = (int)(info & 0xffffu); start = (int)(info >> 16) - cnt; }
     }
-    // pass 2: the first arriver of each bucket reserves its range and counts the bucket in its size class
+    // pass 2: the first arriver of each bucket reserves its range and counts the bucket in its slot class
     __device__ __forceinline__ void alloc_buckets_ro() {
         int *szc = size_count();
         for (int p = tid; p < N; p += NT) {
@@ -609,24 +634,34 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                 } else {
                     tinfo[slot] = cnt | (off << 16);
                 }
-                if (cnt > 1u) atomicAdd(&szc[cnt < 33u ? cnt : 33u], 1);
+                if (cnt > 1u) atomicAdd(&szc[cls_of(cnt)], 1);
             }
         }
     }
-    // pass 3: scatter of the members; the first arriver also files the bucket in the sorted work list.
+    // pass 3: scatter of the members; the first arriver also files the bucket in the class-sorted work list.
     // A point alone in its cell cannot collide and gets its plane collision right away.
     __device__ __forceinline__ void scatter_members_ro() {
         const unsigned FULL = 0xffffffffu;
         uint16_t *wl = worklist();
         int *szf = size_fill();
-        // every warp scans the class counters itself (lane l <-> class 33 - l): first work-list index of each class
-        int cls_off = size_count()[33 - lane];                       // classes 33 .. 2
+        // every warp scans the class counters itself (lane l <-> class l): first work-list index of each class; warp 0
+        // also leaves the tables collide_buckets() reads: per class its first group and first item, and the group total
+        int cls_off = lane < NSC ? size_count()[lane] : 0;
         {
-            int incl = cls_off;
+            const int cnt_l = cls_off;
+            const int cap_l = cls_cap(lane < NSC ? lane : 0);
+            int incl = cnt_l, gincl = (cnt_l + cap_l - 1) / cap_l;
+            const int g_l = gincl;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-            if (tid == 31) misc[1] = incl;                           // number of buckets with >= 2 members
-            cls_off = incl - cls_off;
+            for (int o = 1; o < 16; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o), w = __shfl_up_sync(FULL, gincl, o);
+                if (lane >= o) { incl += v; gincl += w; }
+            }
+            cls_off = incl - cnt_l;
+            if (warp == 0) {
+                if (lane < NSC) { group_off()[lane] = gincl - g_l; item_off()[lane] = cls_off; }
+                if (lane == NSC - 1) misc[1] = gincl;                // number of groups
+            }
         }
         const int nrows = ORDERED ? HASH_ROWS : (N + NT - 1) / NT;
         for (int i = 0; i < nrows; i++) {
@@ -654,8 +689,8 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                 cnt = old & 0xffffu; at = old >> 16;
             }
             const bool files = on && (s & 0x8000u) && cnt > 1u;
-            const int cls = files ? (cnt < 33u ? (int)cnt : 33) : 33;
-            const int off = __shfl_sync(FULL, cls_off, 33 - cls);
+            const int cls = files ? cls_of(cnt) : 0;
+            const int off = __shfl_sync(FULL, cls_off, cls);
             if (files) wl[off + atomicAdd(&szf[cls], 1)] = (uint16_t)(s & 0x7fffu);
             if (on) {
                 if (cnt == 1u) plane_point(p);
@@ -681,61 +716,42 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     __device__ __forceinline__ void collide_buckets() {
         const unsigned FULL = 0xffffffffu;
         for (int j = tid; j < P.ev_words; j += NT) ev[j] = 0u;   // pslot is dead from here on: its storage becomes the spring queue
-        const int nwork = misc[1];
+        const int ngroups = misc[1];
         const uint16_t *wl = worklist();
         const uint16_t *lst = ordered_list();
+        const int my_goff = lane < NSC ? group_off()[lane] : 0x7fffffff, my_ioff = lane < NSC ? item_off()[lane] : 0,
+                  my_cnt = lane < NSC ? size_count()[lane] : 0;
         int badq = 0;                                            // coincident points (reference: ZeroDivisionError)
-        long long tw = prof_on ? clock64() : 0;
         for (;;) {
-            // ---- take the longest run of work-list buckets that fits the 32 lanes (one bucket if it is larger) ----
-            int cur = 0;
-            if (lane == 0) cur = *(volatile int *)&misc[6];
-            cur = __shfl_sync(FULL, cur, 0);
-            int k = 0, cnt_i = 0, start_i = 0, incl = 0;
-            for (;;) {
-                if (cur >= nwork) break;
-                const int item = cur + lane;
-                cnt_i = 64; start_i = 0;
-                if (item < nwork) bucket_range(tinfo[wl[item]], cnt_i, start_i);
-                incl = min(cnt_i, 64);
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                k = __popc(__ballot_sync(FULL, incl <= 32));     // prefix sums are increasing: the fitting items are a prefix
-                int old = 0;
-                if (lane == 0) old = atomicCAS(&misc[6], cur, cur + (k ? k : 1));
-                old = __shfl_sync(FULL, old, 0);
-                if (old == cur) break;
-                cur = old;
-            }
-            if (cur >= nwork) break;
-            if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[4], (unsigned long long)(t - tw)); tw = t; }
-            if (k == 0) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&misc[6], 1);
+            g = __shfl_sync(FULL, g, 0);
+            if (g >= ngroups) break;
+            // class of group g: the last class whose first group is <= g (empty classes share the offset of the next one)
+            const int c = __popc(__ballot_sync(FULL, my_goff <= g)) - 1;
+            const int gi = g - __shfl_sync(FULL, my_goff, c);
+            const int cap = cls_cap(c), slot = cls_slot(c);
+            const int item0 = __shfl_sync(FULL, my_ioff, c) + gi * cap;
+            const int k = min(cap, __shfl_sync(FULL, my_cnt, c) - gi * cap);
+            if (c == 0) {
                 // a pile of more than 32 points: members in 2 or 4 registers per lane, or the shared-memory path
-                const int cnt = __shfl_sync(FULL, cnt_i, 0), start = __shfl_sync(FULL, start_i, 0);
+                int cnt, start;
+                bucket_range(tinfo[wl[item0]], cnt, start);
                 if (prof_on && lane == 0) { atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)cnt * (unsigned long long)(cnt - 1)); atomicAdd((unsigned long long *)&pacc[5], 1ull); }
                 if (!ORDERED) order_bucket(start, cnt);
                 if (cnt <= 64) replay_bucket_regs<2>(lst, start, cnt, 0);
                 else if (cnt <= 128) replay_bucket_regs<4>(lst, start, cnt, 0);
                 else replay_bucket_smem(lst, start, cnt, 0);
                 __syncwarp();
-                if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[6], (unsigned long long)(t - tw)); tw = t; }
                 continue;
             }
             // ---- lane -> (segment, member) ----
-            const unsigned ends = __reduce_or_sync(FULL, lane < k ? 1u << (incl - 1) : 0u);   // last lane of every segment
-            const int total = __shfl_sync(FULL, incl, k - 1);
-            const int my_i = __popc(ends & ((1u << lane) - 1u));
-            const int s_end = __shfl_sync(FULL, incl, my_i), s_cnt = __shfl_sync(FULL, cnt_i, my_i), s_start = __shfl_sync(FULL, start_i, my_i);
-            const bool valid = lane < total;
-            const int seg_cnt = valid ? s_cnt : 0, seg_base = valid ? s_end - s_cnt : 0, li = lane - seg_base;
+            const int seg = (lane * cls_mul(c)) >> 8, seg_base = seg * slot, li = lane - seg_base;
+            int seg_cnt = 0, s_start = 0;
+            if (seg < k) bucket_range(tinfo[wl[item0 + seg]], seg_cnt, s_start);
+            const bool valid = li < seg_cnt;
+            if (!valid) seg_cnt = 0;
             const int maxcnt = __reduce_max_sync(FULL, seg_cnt);
-            if (prof_on) {   // members, buckets and ordered pair tests n(n-1) of this group (SURVEY.md 8d's P)
-                const int pairs = __reduce_add_sync(FULL, valid ? seg_cnt - 1 : 0);
-                if (lane == 0) {
-                    atomicAdd((unsigned long long *)&pacc[14], (unsigned long long)total); atomicAdd((unsigned long long *)&pacc[11], (unsigned long long)k);
-                    atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)pairs);
-                }
-            }
             int mine = valid ? lstA[s_start + li] : 0;
             if (!ORDERED) {
                 // members into point-index order: rank inside the segment, permute through the bucket's lstB range
@@ -753,12 +769,22 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                     if (valid) mine = lstB[s_start + li];
                 }
             }
-            P4 Pm = pos[mine];
+            P4 Pm = mk4(T(0), T(0), T(0), T(1));
+            if (valid) Pm = pos[mine];                               // idle lanes read nothing: another warp may be writing any point
             bool dirty = false;
-            const unsigned segmask = seg_cnt >= 32 ? FULL : ((1u << seg_cnt) - 1u);
+            const unsigned segmask = slot >= 32 ? FULL : ((1u << slot) - 1u);
             // bit j <=> member j of my segment is a subject I am a candidate for: it exists, is not pinned (pinned
             // members never move and are skipped as subjects, cloth.pyx:314-315) and is not me
-            const unsigned subj = (__ballot_sync(FULL, valid && Pm.w == T(0)) >> seg_base) & segmask & ~(1u << li);
+            const unsigned subj_seg = (__ballot_sync(FULL, valid && Pm.w == T(0)) >> seg_base) & segmask & ~(1u << li);
+            const unsigned subj = valid ? subj_seg : 0u;             // the padding lanes of a slot are nobody's candidate
+            if (prof_on) {   // members, buckets and ordered pair tests n(n-1) of this group (SURVEY.md 8d's P)
+                const int pairs = __reduce_add_sync(FULL, valid ? seg_cnt - 1 : 0);
+                const unsigned vm = __ballot_sync(FULL, valid);
+                if (lane == 0) {
+                    atomicAdd((unsigned long long *)&pacc[14], (unsigned long long)__popc(vm)); atomicAdd((unsigned long long *)&pacc[11], (unsigned long long)k);
+                    atomicAdd((unsigned long long *)&pacc[15], (unsigned long long)pairs); atomicAdd((unsigned long long *)&pacc[6], (unsigned long long)maxcnt);
+                }
+            }
 #pragma unroll 1
             for (int j = 0; j < maxcnt; j++) {
                 const int src = seg_base + j;
@@ -811,7 +837,6 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
                 if (dirty) pos[mine] = Pm;
             }
             __syncwarp();
-            if (prof_on && lane == 0) { const long long t = clock64(); atomicAdd((unsigned long long *)&pacc[6], (unsigned long long)(t - tw)); tw = t; }
         }
         if (badq) misc[3] = 1;
     }
@@ -992,6 +1017,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             }
             int cand = 0x7fffffff;
             nmove += moved ? 1 : 0;
+            __syncwarp();                                            // every lane has read its points before lane 0 stores
             if (lane == 0 && moved) { if (!pa) pos[a] = Pa; if (!pb) pos[q] = Pb; }
             {
                 // re-test my incident spring against the updated end point, in registers.  The squared terms make
@@ -1011,6 +1037,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             s = nxt;
         }
         // the queue is left clean for the next substep
+        __syncwarp();
         for (int j = lane; j < nw; j += 32) ev[j] = 0u;
         if (prof_on && lane == 0) { pacc[12] += npop; pacc[13] += nmove; }
     }
@@ -1025,7 +1052,8 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         if (FAST) {
             const bool on = cur != 0xffffffffu;
             const int a = on ? (int)(cur & 0xfffu) : 0, q = on ? (int)((cur >> 12) & 0xfffu) : 0, k = (cur >> 24) & 7u;
-            const P4 Pa = pos[a], Pb = pos[q];
+            P4 Pa = mk4(T(0), T(0), T(0), T(1)), Pb = Pa;            // idle lanes: a pinned dummy spring, nothing read or written
+            if (on) { Pa = pos[a]; Pb = pos[q]; }
             float c11, ct2;
             if (REST_TABLE) { c11 = (float)rst_tab * 1.1f; const float ct = (float)rst_tab * (float)P.tear_thresh; ct2 = ct * ct; }
             else { const float2 c = kc[k]; c11 = c.x; ct2 = c.y; }

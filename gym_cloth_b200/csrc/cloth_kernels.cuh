@@ -11,7 +11,8 @@ namespace clothb200 {
 extern std::atomic<long long> g_launch_count;   // defined in cloth_abi.cu
 extern int g_debug_flags;
 extern int g_force_slots, g_force_slice;         // tests: clothb200_debug_set_slicing
-extern long long *g_prof_ptr;                    // debug: per-env phase counters (clothb200_debug_set_profile)
+extern long long *g_prof_ptr;
+#define CLOTHB200_MAX_DEVICES 64                    // debug: per-env phase counters (clothb200_debug_set_profile)
 void set_cuda_error(cudaError_t e, const char *where);
 
 // ------------------------------------------------------------------------------------------------
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
             double rad = P.grip_radius;
             for (int tries = 0; ngrab == 0 && tries < 4096; tries++) { rad += 0.02; ngrab = c.grab_top(plan.gx, plan.gy, rad); }
         }
-        if (A.grab_mask && i_begin == 0) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
+        if (A.grab_mask && i_begin == 0) { c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5)); c.sync(); }
         // _pull thresholds (cloth_env.py:352-367, 472-475): `i < t` for integer i <=> i < ceil(t)
         const double iu = A.iters_up_env ? A.iters_up_env[env] : P.iu;
         const double t1 = iu + P.iur, t2 = t1 + (double)plan.iters_pull, t3 = t2 + P.igr, t4 = t3 + P.ir;
@@ -438,21 +439,27 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
     typedef ClothCTA<T, NT, WC, RT, COL> CTA;
     const size_t smem = CTA::smem_bytes(P.N, P.table_size, P.ev_words);
     auto kern = cloth_step_kernel<T, NT, WC, RT, COL>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    // cudaFuncSetAttribute and occupancy are per device: one process may drive several GPUs (SURVEY.md 8(e) allows one
+    // process with a stream per device), so both caches are keyed by the current device
+    static std::atomic<size_t> configured[CLOTHB200_MAX_DEVICES];
+    static std::atomic<int> slots_of[CLOTHB200_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= CLOTHB200_MAX_DEVICES) return CLOTHB200_ERR_UNSUPPORTED;
+    if (smem > configured[dev].load()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(smem)"); return CLOTHB200_ERR_UNSUPPORTED; }
-        configured = smem;
+        configured[dev].store(smem);
     }
     if (A.slice > 0) {
         // time-sliced mode: a persistent grid, one CTA per resident slot; pointless when every cloth has its own slot
-        static int slots = 0;
+        int slots = slots_of[dev].load();
         if (!slots) {
-            int occ = 0, dev = 0, sms = 0;
-            cudaGetDevice(&dev);
+            int occ = 0, sms = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess || occ < 1) occ = 1;
             slots = occ * sms;
+            slots_of[dev].store(slots);
         }
         const int use_slots = g_force_slots > 0 ? g_force_slots : slots;
         if (A.n_env > use_slots) {

@@ -18,6 +18,14 @@ def reduce_max(values, device):
     return t.tolist()
 
 
+def reduce_sum(values, device):
+    """Sum over ranks of a list of counts."""
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
 def episode_stats(coverage, done, device):
     """Sufficient statistics of per-env results summed over ranks: (sum coverage, sum coverage^2, n, n_done)."""
     c = coverage.double()

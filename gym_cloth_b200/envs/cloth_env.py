@@ -18,6 +18,8 @@ equally distributed, draws - 150 531 draws per reset and environment are not fre
 import copy
 import pickle
 
+import contextlib
+
 import numpy as np
 import torch
 import yaml
@@ -75,7 +77,8 @@ class BatchedClothEnv(object):
     streams, so results do not depend on how the batch is sharded.
     """
 
-    def __init__(self, cfg, n_env, dtype="f32", device=None, seed=None, env_offset=0, dom_rand_draws=False):
+    def __init__(self, cfg, n_env, dtype="f32", device=None, seed=None, env_offset=0, dom_rand_draws=False,
+                 mode=_l.MODE_REFERENCE_ORDER):
         self.cfg = load_cfg(cfg)
         cfg = self.cfg
         self.P = _l.params_from_cfg(cfg)
@@ -100,13 +103,14 @@ class BatchedClothEnv(object):
         self.max_actions = env["max_actions"]
         self.grip_radius = env["grip_radius"]
         self.dom_rand_draws = dom_rand_draws
+        self.time_resets = False          # True: reset() leaves the GPU's own busy time of the reset in reset_device_ms
         self.N = self.P.num_width_points * self.P.num_height_points
         self.action_space = _Box([-1., -1., -1., -1.], [1., 1., 1., 1.])
         lim = 100
         self.observation_space = _Box(-lim * np.ones(3 * self.N), lim * np.ones(3 * self.N))
         self.cloth = BatchedCloth(self.P, self.n_env, dtype=self.torch_dtype, device=device,
                                   init_type="tier1" if self.init_type == "tier3" else self.init_type,
-                                  noise=np.zeros(self.N) if self.init_type == "tier2" else None)
+                                  noise=np.zeros(self.N) if self.init_type == "tier2" else None, mode=mode)
         self.device = self.cloth.device
         self.renderer = None
         if self.obs_type == "blender":
@@ -145,6 +149,19 @@ class BatchedClothEnv(object):
         e = torch.as_tensor(envs, device=self.device); p = torch.as_tensor(pidx, device=self.device)
         return self.cloth.pos[e, p, :2].double().cpu().numpy()
 
+    @contextlib.contextmanager
+    def _timed(self):
+        """CUDA events around one device call of a reset (reset_device_ms: how long the GPU itself worked)."""
+        ev = getattr(self, "_reset_events", None)
+        if ev is None:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        ev.append((a, b))
+
     def _step_subset(self, envs, actions, initialize, iters_up=None):
         """step(action, initialize) for a subset of environments (host decode = CPython arithmetic)."""
         c = self.cloth
@@ -160,7 +177,8 @@ class BatchedClothEnv(object):
         c.plans.copy_(host)
         c.env_order, c.n_env = order, len(envs)
         try:
-            c.step_plans(c.plans, initialize=initialize)
+            with self._timed():
+                c.step_plans(c.plans, initialize=initialize)
         finally:
             c.env_order, c.n_env, c.iters_up_env = old_order, old_n, old_iu
 
@@ -170,7 +188,8 @@ class BatchedClothEnv(object):
         old_order, old_n = c.env_order, c.n_env
         c.env_order, c.n_env = order, len(envs)
         try:
-            c.update(n_updates)
+            with self._timed():
+                c.update(n_updates)
         finally:
             c.env_order, c.n_env = old_order, old_n
 
@@ -193,6 +212,7 @@ class BatchedClothEnv(object):
         n = len(envs)
         if n == 0:
             return c.obs
+        self._reset_events = [] if self.time_resets else None
         # Cloth.__init__ (cloth.pyx:75, 94-130): init_side is always drawn, tier2 draws the x-noise
         sides = np.array([self.rngs[e].rand() > 0.5 for e in envs])
         self.init_side[envs] = sides
@@ -214,6 +234,10 @@ class BatchedClothEnv(object):
         c.prev_coverage[idx_t] = c.coverage[idx_t]
         if self.dom_rand_draws or self.renderer is not None:
             self._draw_dom_rand(envs)
+        if self._reset_events is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+            self.reset_device_ms = sum(a.elapsed_time(b) for a, b in self._reset_events)
+            self._reset_events = None
         return c.obs if self.renderer is None else self.image_obs()
 
     def _draw_dom_rand(self, envs):
@@ -383,6 +407,14 @@ class BatchedClothEnv(object):
     def get_random_action(self, atype="over_xy_plane"):   # cloth_env.py:989-1018
         if atype == "over_xy_plane":
             return np.stack([self.action_space.sample() for _ in range(self.n_env)])
+        if atype == "touch_cloth":
+            # the reference supports this only without delta actions (assert at :1006); with them the pick point is a
+            # mesh point drawn from np_random as there and (dx, dy) come from the action space
+            pidx = np.array([r.randint(self.N) for r in self.rngs])
+            xy = self._points_xy(np.arange(self.n_env), pidx)
+            a = np.stack([self.action_space.sample() for _ in range(self.n_env)]).astype(np.float64)
+            a[:, 0] = (xy[:, 0] - 0.5) * 2; a[:, 1] = (xy[:, 1] - 0.5) * 2
+            return a
         raise ValueError(atype)
 
     # ------------------------------------------------------------------ state pool (fast synthetic resets)

@@ -129,3 +129,169 @@ def highest_point_actions(benv, top_k=5, generator=None):
     targ = torch.stack([tx, orig[:, 1]], dim=1)
     act = torch.cat([(xy - 0.5) * 2.0, (targ - xy) * 0.90], dim=1)
     return act.to(benv.torch_dtype)
+
+
+# ---------------------------------------------------------------------------------------------- wrinkle policy
+def _wrinkle_levels():
+    """The z levels is_point_on_top scans (analytic.py:571-586): 1, 1-0.02, ... by repeated subtraction while > 0."""
+    out = []
+    z = 1
+    while z > 0:
+        out.append(z)
+        z -= 0.02
+    return np.array(out, np.float64)
+
+
+def _neighbors(r, c, h, w):
+    """get_neighbors (analytic.py:588-612), in the reference's order (its `c < h - 1` included)."""
+    pts = [r * w + c]
+    if r > 0 and c > 0:
+        pts.append((r - 1) * w + c - 1)
+    if r > 0:
+        pts.append((r - 1) * w + c)
+    if c > 0:
+        pts.append(r * w + c - 1)
+    if r < h - 1 and c < w - 1:
+        pts.append((r + 1) * w + c + 1)
+    if r < h - 1:
+        pts.append((r + 1) * w + c)
+    if c < h - 1:
+        pts.append(r * w + c + 1)
+    if r > 0 and c < w - 1:
+        pts.append((r - 1) * w + c + 1)
+    if r < h - 1 and c > 0:
+        pts.append((r + 1) * w + c - 1)
+    return pts
+
+
+def _wrinkle_pull(center, wrinkle_pt, xs, ys):
+    """analytic.py:676-720: pull perpendicular to the wrinkle, from the cloth point nearest to where that line (or the
+    diagonal it is closest to) leaves the unit square.  center / wrinkle_pt: (x, y); xs, ys: all points."""
+    if wrinkle_pt[0] == center[0]:
+        slope = 1000
+    else:
+        slope = (wrinkle_pt[1] - center[1]) / (wrinkle_pt[0] - center[0])
+    perp_slope = -1 / slope
+    r2 = np.sqrt(2)
+    if perp_slope > r2 + 1 or perp_slope < -(r2 + 1):
+        x1 = (1 - center[1]) / perp_slope + center[0]; y1 = 1
+        x2 = (-center[1]) / perp_slope + center[0]; y2 = 0
+    elif perp_slope > 1 and perp_slope < r2 + 1:
+        x1, y1, x2, y2 = 1, 1, 0, 0
+    elif perp_slope < r2 - 1 and perp_slope > -(r2 - 1):
+        y1 = perp_slope * (1 - center[0]) + center[1]; x1 = 1
+        y2 = perp_slope * (-center[0]) + center[1]; x2 = 0
+    else:
+        x1, y1, x2, y2 = 0, 1, 1, 0
+    i1 = int(np.argmin(np.sqrt((x1 - xs) ** 2 + (y1 - ys) ** 2)))
+    i2 = int(np.argmin(np.sqrt((x2 - xs) ** 2 + (y2 - ys) ** 2)))
+    d1 = np.sqrt((center[0] - xs[i1]) ** 2 + (center[1] - ys[i1]) ** 2)
+    d2 = np.sqrt((center[0] - xs[i2]) ** 2 + (center[1] - ys[i2]) ** 2)
+    if d1 < d2 or xs[i2] < 0.01 or xs[i2] > 0.99 or ys[i2] < 0.01 or ys[i2] > 0.99:
+        x, y = xs[i1], ys[i1]; dx, dy = x1 - x, y1 - y
+    else:
+        x, y = xs[i2], ys[i2]; dx, dy = x2 - x, y2 - y
+    return (2 * (x - 0.5), 2 * (y - 0.5), dx, dy)
+
+
+class WrinklesPolicy(Policy):
+    """examples/analytic.py:551-720 on the ground-truth state: the point whose 3x3 neighbourhood deviates most in height
+    (among the points that are on top of the cloth where they are) is the wrinkle's centre, its most deviating neighbour
+    gives the wrinkle's direction, and the cloth is pulled perpendicular to it towards the edge of the plane."""
+
+    def get_action(self, obs, t):
+        cloth = self.env.cloth
+        pts = cloth.pts
+        w = h = int(round(len(pts) ** 0.5))
+        xs = np.array([p.x for p in pts]); ys = np.array([p.y for p in pts]); zs = np.array([p.z for p in pts])
+        levels = _wrinkle_levels()
+        deviation = []
+        for i in range(len(pts)):
+            near = ((xs - xs[i]) * (xs - xs[i]) + (ys - ys[i]) * (ys - ys[i])) < 0.0002      # includes i itself
+            band = np.abs(zs[near][:, None] - levels[None, :]) < 2 * 0.02                       # [members, levels]
+            hit = band.any(axis=0)
+            on_top = bool(hit.any()) and bool(abs(zs[i] - levels[int(np.argmax(hit))]) < 2 * 0.02)
+            if on_top:
+                r, c = divmod(i, w)
+                points = np.array([zs[x] for x in _neighbors(r, c, h, w)])
+                deviation.append(np.sum(np.abs(points - np.mean(points))))
+            else:
+                deviation.append(0)
+        p = deviation.index(max(deviation))
+        c = p % w
+        r = (p - c) // w
+        indices = _neighbors(r, c, h, w)
+        indices.remove(r * w + c)
+        mx = max(indices, key=lambda index: deviation[index])
+        return _wrinkle_pull((xs[p], ys[p]), (xs[mx], ys[mx]), xs, ys)
+
+
+_NB_CACHE = {}
+
+
+def _neighbor_table(w, device):
+    key = (w, str(device))
+    if key not in _NB_CACHE:
+        tab = np.full((w * w, 9), -1, np.int64)
+        for i in range(w * w):
+            nb = _neighbors(i // w, i % w, w, w)
+            tab[i, :len(nb)] = nb
+        _NB_CACHE[key] = torch.from_numpy(tab).to(device)
+    return _NB_CACHE[key]
+
+
+def wrinkle_actions(benv, chunk=128):
+    """Batched WrinklesPolicy: [n_env, 4] actions (clip space), float64, computed on the device from the state tensors
+    (pairwise tests in chunks of `chunk` environments).  Same decisions as the single-environment class up to ties."""
+    pos = benv.cloth.pos
+    dev = pos.device
+    n, N = benv.n_env, benv.N
+    w = int(round(N ** 0.5))
+    levels = torch.from_numpy(_wrinkle_levels()).to(dev)
+    tab = _neighbor_table(w, dev)
+    valid = tab >= 0
+    tabc = tab.clamp(min=0)
+    out = torch.empty(n, 4, dtype=torch.float64, device=dev)
+    r2 = 2.0 ** 0.5
+    for s in range(0, n, chunk):
+        P = pos[s:s + chunk, :, :3].double()
+        m = P.shape[0]
+        ar = torch.arange(m, device=dev)
+        x, y, z = P[:, :, 0], P[:, :, 1], P[:, :, 2]
+        dxm = x[:, None, :] - x[:, :, None]; dym = y[:, None, :] - y[:, :, None]
+        near = (dxm * dxm + dym * dym) < 0.0002                                            # [m, N, N]
+        band = (z[:, :, None] - levels[None, None, :]).abs() < 2 * 0.02                     # [m, N, L]
+        hit = torch.bmm(near.to(torch.float32), band.to(torch.float32)) > 0                 # [m, N, L]: some near point in the band
+        first = torch.argmax(hit.to(torch.int8), dim=2)
+        on_top = hit.any(dim=2) & torch.gather(band, 2, first[:, :, None])[:, :, 0]
+        zn = z[:, tabc]                                                                     # [m, N, 9]
+        cnt = valid.sum(1).to(torch.float64)[None, :]
+        mean = (zn * valid[None]).sum(2) / cnt
+        dev_map = ((zn - mean[:, :, None]).abs() * valid[None]).sum(2)
+        dev_map = torch.where(on_top, dev_map, torch.zeros_like(dev_map))
+        p = torch.argmax((dev_map == dev_map.max(dim=1, keepdim=True).values).to(torch.int8), dim=1)   # first maximum
+        nb = tab[p][:, 1:]; nbv = nb >= 0                                                   # neighbours of the centre, self removed
+        nd = torch.where(nbv, dev_map[ar[:, None], nb.clamp(min=0)], torch.full_like(nb, -1.0, dtype=torch.float64))
+        k = torch.argmax((nd == nd.max(dim=1, keepdim=True).values).to(torch.int8), dim=1)
+        q = nb[ar, k]
+        cx, cy = x[ar, p], y[ar, p]
+        wx, wy = x[ar, q], y[ar, q]
+        slope = torch.where(wx == cx, torch.full_like(cx, 1000.0), (wy - cy) / (wx - cx))
+        ps = -1.0 / slope
+        ns = (ps > r2 + 1) | (ps < -(r2 + 1))
+        ne = (ps > 1) & (ps < r2 + 1) & ~ns
+        ew = (ps < r2 - 1) & (ps > -(r2 - 1)) & ~ns & ~ne
+        one, zero = torch.ones_like(cx), torch.zeros_like(cx)
+        x1 = torch.where(ns, (1 - cy) / ps + cx, torch.where(ne, one, torch.where(ew, one, zero)))
+        y1 = torch.where(ns, one, torch.where(ne, one, torch.where(ew, ps * (1 - cx) + cy, one)))
+        x2 = torch.where(ns, (-cy) / ps + cx, torch.where(ne, zero, torch.where(ew, zero, one)))
+        y2 = torch.where(ns, zero, torch.where(ne, zero, torch.where(ew, ps * (-cx) + cy, zero)))
+        i1 = torch.argmin(((x1[:, None] - x) ** 2 + (y1[:, None] - y) ** 2).sqrt(), dim=1)
+        i2 = torch.argmin(((x2[:, None] - x) ** 2 + (y2[:, None] - y) ** 2).sqrt(), dim=1)
+        ax1, ay1, ax2, ay2 = x[ar, i1], y[ar, i1], x[ar, i2], y[ar, i2]
+        d1 = ((cx - ax1) ** 2 + (cy - ay1) ** 2).sqrt(); d2 = ((cx - ax2) ** 2 + (cy - ay2) ** 2).sqrt()
+        use1 = (d1 < d2) | (ax2 < 0.01) | (ax2 > 0.99) | (ay2 < 0.01) | (ay2 > 0.99)
+        gx = torch.where(use1, ax1, ax2); gy = torch.where(use1, ay1, ay2)
+        tx = torch.where(use1, x1, x2); ty = torch.where(use1, y1, y2)
+        out[s:s + chunk] = torch.stack([2 * (gx - 0.5), 2 * (gy - 0.5), tx - gx, ty - gy], dim=1)
+    return out

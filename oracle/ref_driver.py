@@ -135,3 +135,63 @@ def cpu_env_steps(kind, states, actions, cores=None):
     return {"value": len(jobs) / dt, "substeps_per_s": sub / dt, "seconds": dt, "cores": cores, "n": len(jobs),
             "substeps": sub, "coverage": [r[1] for r in res], "states": [(r[3], r[4]) for r in res],
             "tear": [r[5] for r in res], "oob": [r[6] for r in res], "n_updates": [r[0] for r in res]}
+
+
+# ------------------------------------------------------------------ episodes: one process per environment, K steps each
+def _episode_worker(kind, i, pool_pos, pool_prev, start, raw, pick, choice, W, max_actions, barrier, q):
+    """Environment i of bench.py's workload on one host core: W untimed + K timed env.step calls.  `raw[t]` is the drawn
+    action, `pick[t]` the mesh point its grip is aimed at (None: use raw as it is), `choice[t]` the pool state it restarts
+    from when the step ends its episode (ClothEnv._terminal, cloth_env.py:682-715: tear, out of bounds, coverage > 0.92,
+    max_actions)."""
+    pos, prev = pool_pos[start].copy(), pool_prev[start].copy()
+    steps = 0
+    rec = []
+    t0 = None
+    for t in range(len(raw)):
+        if t == W:
+            barrier.wait()
+            t0 = time.perf_counter()
+        a = np.array(raw[t], np.float64)
+        if pick is not None:
+            a[0] = (pos[pick[t], 0] - 0.5) * 2; a[1] = (pos[pick[t], 1] - 0.5) * 2
+        r = _worker((kind, pos, prev, a))
+        n, cov, dt, pos, prev, tear, oob = r
+        steps += 1
+        done = tear or oob or cov > 0.92 or steps >= max_actions
+        if t >= W:
+            rec.append((n, cov, dt, int(done), int(n == 0)))
+        last = pos
+        if done:
+            pos, prev = pool_pos[choice[t]].copy(), pool_prev[choice[t]].copy()
+            steps = 0
+    t1 = time.perf_counter()
+    q.put((i, t0, t1, rec, last if len(raw) == 1 else None))
+
+
+def cpu_env_episodes(kind, pool_pos, pool_prev, starts, raw, pick, choice, warmup, cores=None, max_actions=10):
+    """len(starts) environments, one host process each (the reference's own scaling model: one CPU per analytic.py
+    process, analysis/README.md:9-11), each doing `warmup` untimed and raw.shape[0]-warmup timed env.step calls with
+    no synchronisation between environments.  The clock runs from the moment every process has finished its warm-up to
+    the moment the last one finishes.  raw [T, n, 4], pick [T, n] or None, choice [T, n]."""
+    n = len(starts)
+    cores = cores or os.cpu_count() or 1
+    assert n <= cores, "one environment per core"
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(n)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_episode_worker, args=(kind, i, pool_pos, pool_prev, starts[i], raw[:, i], None if pick is None else pick[:, i],
+                                                       choice[:, i], warmup, max_actions, barrier, q)) for i in range(n)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get() for _ in procs)
+    for p in procs:
+        p.join()
+    t0 = min(r[1] for r in res); t1 = max(r[2] for r in res)
+    K = raw.shape[0] - warmup
+    rec = [r[3] for r in res]
+    sub = sum(x[0] for e in rec for x in e)
+    busy = sum(x[2] for e in rec for x in e)
+    return {"value": n * K / (t1 - t0), "substeps_per_s": sub / (t1 - t0), "seconds": t1 - t0, "cores": n, "n": n * K, "steps": K,
+            "substeps": sub, "core_busy_frac": busy / (n * (t1 - t0)), "coverage": [[x[1] for x in e] for e in rec],
+            "n_updates": [[x[0] for x in e] for e in rec], "done_frac": float(np.mean([x[3] for e in rec for x in e])),
+            "nograb_frac": float(np.mean([x[4] for e in rec for x in e])), "final_pos": [r[4] for r in res]}

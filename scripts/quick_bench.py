@@ -98,8 +98,8 @@ if __name__ == "__main__":
         act = p[:, 10] > 0
         names = ["hooke_verlet", "commit_hash", "alloc", "scatter", "(coll: grab, 4 warps)", "(unused)", "(coll: work, 4 warps)", "collide_buckets", "limit_snap", "limit_resolve"]
         nsub = p[act, 10].sum()
-        print("  collide_buckets per warp: taking work %.0f cyc/substep, working %.0f cyc/substep (sums over the 4 warps / 4)" % (p[act, 4].sum() / nsub / 4, p[act, 6].sum() / nsub / 4))
-        p[:, 4] = 0; p[:, 6] = 0
+        print("  collide_buckets: near members/substep %.1f, replay rounds/substep %.1f (warp groups x subjects)" % (p[act, 4].sum() / nsub, p[act, 6].sum() / nsub))
+        p[:, 4] = 0; p[:, 6] = 0                         # event counters, not cycles (5 = piles: small, left in)
         tot = p[act, :10].sum()
         print("%s: %.1f ms; active envs %d; substeps %d; cycles/substep/CTA %.0f" % (str(dt), e0.elapsed_time(e1), act.sum(), nsub, tot / nsub))
         for i, nm in enumerate(names):

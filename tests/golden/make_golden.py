@@ -267,7 +267,7 @@ def gen_policy(out, tier=1, seed=1337, episodes=2, kind="oracle", max_t=None):
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         import analytic
-    policy = analytic.OracleCornerPolicy() if kind == "oracle" else analytic.HighestPointPolicy()
+    policy = {"oracle": analytic.OracleCornerPolicy, "highest": analytic.HighestPointPolicy, "wrinkle": analytic.WrinklesPolicy}[kind]()
     policy.set_env_cfg(env, env.cfg)
     d = {"tier": tier, "seed": seed}
     np.random.seed(seed)
@@ -440,7 +440,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "state", "bench_pool"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "policy_wrinkle", "state", "bench_pool"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -462,6 +462,8 @@ def main():
         sys.exit(max(rc))
     if a.what == "policy_highest":
         return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="highest", max_t=3)
+    if a.what == "policy_wrinkle":      # WrinklesPolicy (analytic.py:551-720): ground-truth state, no image, no RNG
+        return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="wrinkle", max_t=3)
     {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy, "state": gen_state, "bench_pool": gen_bench_pool}.get(
         a.what, lambda out: gen_env(out, a.tier, a.seed, a.actions))(a.out)
 

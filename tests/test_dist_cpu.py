@@ -1,5 +1,5 @@
 """world_size-2 gloo test (CPU) of the multi-process path: global-id sharding of the synthetic actions is invariant to
-the number of ranks, timing is reduced with MAX and episode statistics with SUM - the only collectives bench.py uses."""
+the number of ranks, timing is reduced with MAX and episode statistics with SUM - the only collectives bench.py uses (through gym_cloth_b200/dist.py)."""
 import os
 import socket
 
@@ -19,13 +19,15 @@ def _worker(rank, world, port, n_per_rank, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
-    from gym_cloth_b200.dist import episode_stats, reduce_max, shard_bounds
+    from gym_cloth_b200.dist import episode_stats, reduce_max, reduce_sum, shard_bounds
     lo, hi = shard_bounds(n_per_rank, rank)
-    a = torch.from_numpy(bench.actions_for_step(11, 2, lo, hi))
+    raw, pick = bench.draw_actions(11, 2, lo, hi)
+    a = torch.cat([torch.from_numpy(raw), torch.from_numpy(pick).double()[:, None]], 1)
     gathered = [torch.zeros_like(a) for _ in range(world)]
     dist.all_gather(gathered, a)
-    full = torch.from_numpy(bench.actions_for_step(11, 2, 0, n_per_rank * world))
-    ok = torch.equal(torch.cat(gathered), full)
+    raw_f, pick_f = bench.draw_actions(11, 2, 0, n_per_rank * world)
+    full = torch.cat([torch.from_numpy(raw_f), torch.from_numpy(pick_f).double()[:, None]], 1)
+    ok = torch.equal(torch.cat(gathered), full) and reduce_sum([rank + 1, 5], "cpu") == [3.0, 10.0]
     tmax = reduce_max([10.0 + rank, 3.0 - rank], "cpu")
     cov = torch.full((n_per_rank,), 0.25 * (rank + 1), dtype=torch.float64)
     st = episode_stats(cov, torch.ones(n_per_rank) * rank, "cpu")

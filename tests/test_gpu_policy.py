@@ -120,3 +120,52 @@ def test_batched_highest_point_policy():
     for t in range(4):
         obs, rew, done, info = benv.step(highest_point_actions(benv, generator=gen))
     assert info["actual_coverage"].mean().item() > cov0
+
+
+def test_wrinkle_policy_matches_reference():
+    """WrinklesPolicy (analytic.py:551-720): the reference's own policy driving the reference env for three actions
+    (tests/golden/policy_wrinkle_t1_s1337.npz); ours must choose the same actions bit for bit and the f64 facade must
+    land in the same states."""
+    from gym_cloth_b200 import cfg_path
+    from gym_cloth_b200.envs import ClothEnv
+    from gym_cloth_b200.policies import WrinklesPolicy
+    g = load_golden("policy_wrinkle_t1_s1337.npz")
+    env = ClothEnv(cfg_path(1), dtype="f64")
+    env.seed(int(g["seed"]))
+    policy = WrinklesPolicy()
+    policy.set_env_cfg(env, env.cfg)
+    obs = env.reset()
+    assert np.array_equal(obs.reshape(-1, 3), g["pos_reset_e0"])
+    for k in range(int(g["episode_lengths"][0])):
+        a = policy.get_action(obs, k)
+        assert np.array_equal(np.array(a, np.float64), g["action_%d" % k]), (k, a, g["action_%d" % k])
+        obs, rew, done, info = env.step(a)
+        rew_ref, done_ref, cov_ref, sim_ref = g["result_%d" % k]
+        assert np.array_equal(obs.reshape(-1, 3), g["pos_%d" % k])
+        assert abs(rew - rew_ref) < 1e-11 and done == bool(done_ref) and info["num_sim_steps"] == int(sim_ref)
+
+
+def test_batched_wrinkle_policy_matches_single_env_policy():
+    from gym_cloth_b200 import cfg_path
+    from gym_cloth_b200.envs import BatchedClothEnv
+    from gym_cloth_b200.policies import WrinklesPolicy, wrinkle_actions
+    n = 48
+    benv = BatchedClothEnv(cfg_path(1), n, dtype="f64", seed=900)
+    benv.reset()
+    acts = wrinkle_actions(benv, chunk=20)
+    assert acts.shape == (n, 4) and acts.dtype == torch.float64
+
+    class _P(object):
+        def __init__(s, xyz): s.x, s.y, s.z = (float(v) for v in xyz)
+
+    class _E(object):
+        pass
+    pol = WrinklesPolicy()
+    for e in (0, 5, 19, 20, 47):
+        env = _E(); env.cloth = _E(); env.cloth.pts = [_P(p) for p in benv.cloth.pos[e, :, :3].cpu().numpy()]
+        pol.set_env_cfg(env, benv.cfg)
+        ref = np.array(pol.get_action(None, 0), np.float64)
+        assert np.allclose(acts[e].cpu().numpy(), ref, atol=1e-9), (e, acts[e], ref)
+    benv.step(acts)                                   # the actions are valid env.step input
+    torch.cuda.synchronize()
+    assert int(((benv.cloth.flags & 4) != 0).sum().item()) <= n // 4        # most grips catch the cloth edge point aimed at
