@@ -362,7 +362,7 @@ def run_ours(args):
     r = arm.run_device(K, W, barrier, flush=flush, sampler=ClockSampler(local))
     clocks = r["clocks"]
     h = arm.run_host(K, min(W, 1), barrier)
-    pairs = arm.measure_pairs(5000) if not coloured else None
+    pairs = arm.measure_pairs(5000) if not (coloured or args.no_pairs) else None
 
     # ---------------- max over ranks of the times, sums of the counts (gym_cloth_b200/dist.py) ----------------
     elapsed_ms, e2e_ms, kernel_ms = D.reduce_max([r["elapsed_ms"], h["seconds"] * 1e3, r["kernel_ms"]], dev)
@@ -571,6 +571,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the extra (untimed, instrumented) step that counts pair tests")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -194,6 +194,12 @@ template <typename A_t> __device__ __forceinline__ int queue_head_remaining(cons
 // ------------------------------------------------------------------------------------------------
 // The per-CTA cloth.  NT threads; WC = compile-time grid width (0 = runtime).
 // ------------------------------------------------------------------------------------------------
+// slot classes of the collision work list (ClothCTA::collide_buckets): SLOT | buckets per warp << 8 | ceil(256 / SLOT) << 16
+static __device__ __constant__ uint32_t kSlotClass[11] = {
+    64u | 1u << 8 | 4u << 16,  32u | 1u << 8 | 8u << 16,  16u | 2u << 8 | 16u << 16, 10u | 3u << 8 | 26u << 16,
+    8u | 4u << 8 | 32u << 16,  7u | 4u << 8 | 37u << 16,  6u | 5u << 8 | 43u << 16,  5u | 6u << 8 | 52u << 16,
+    4u | 8u << 8 | 64u << 16,  3u | 10u << 8 | 86u << 16, 2u | 16u << 8 | 128u << 16};
+
 #define CLOTH_KEY_EMPTY 0x7fffffff
 #define CLOTH_FIRST_NONE 0x7ffffffe
 
@@ -597,12 +603,9 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     __device__ __forceinline__ static int cls_of(uint32_t cnt) {
         return cnt > 32u ? 0 : (cnt > 16u ? 1 : (cnt > 10u ? 2 : (cnt > 8u ? 3 : 12 - (int)cnt)));
     }
-    __device__ __forceinline__ static int pack8(unsigned long long lo, unsigned long long hi, int c) {
-        return (int)(((c < 8 ? lo >> (8 * c) : hi >> (8 * (c - 8)))) & 255ull);
-    }
-    __device__ __forceinline__ static int cls_slot(int c) { return pack8(0x050607080a102040ull, 0x020304ull, c); }
-    __device__ __forceinline__ static int cls_cap(int c) { return pack8(0x0605040403020101ull, 0x100a08ull, c); }
-    __device__ __forceinline__ static int cls_mul(int c) { return pack8(0x342b25201a100804ull, 0x805640ull, c); }   // ceil(256 / SLOT): lane / SLOT = lane * mul >> 8
+    __device__ __forceinline__ static int cls_slot(int c) { return (int)(kSlotClass[c] & 255u); }
+    __device__ __forceinline__ static int cls_cap(int c) { return (int)((kSlotClass[c] >> 8) & 255u); }
+    __device__ __forceinline__ static int cls_mul(int c) { return (int)(kSlotClass[c] >> 16); }   // ceil(256 / SLOT): lane / SLOT = lane * mul >> 8
     __device__ __forceinline__ int *size_count() const { return reinterpret_cast<int *>(lstB); }
     __device__ __forceinline__ int *size_fill() const { return reinterpret_cast<int *>(lstB) + NCLS; }
     __device__ __forceinline__ int *group_off() const { return size_fill() + NSC; }       // first group of each class

@@ -7,7 +7,7 @@ mkdir -p $out
 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 tail -c 600 $out/${tag}_bench.json | head -c 300; echo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-pairs > $out/${tag}_bench_under_ncu.log 2>&1
 # index (among cloth_step_kernel launches) of the last launch that ran longer than 100 ms: a timed env.step
 idx=$(python - <<PY
 import csv
@@ -27,6 +27,17 @@ PY
 )
 echo "full capture of cloth_step_kernel launch #$idx"
 ncu --set full --clock-control none --import-source on -k regex:cloth_step_kernel --launch-skip $idx --launch-count 1 -f -o $out/${tag}_step_kernel \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_full_capture.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-pairs > $out/${tag}_full_capture.log 2>&1
 ncu -i $out/${tag}_step_kernel.ncu-rep --page raw --csv > $out/${tag}_step_kernel_raw.csv 2>/dev/null
 ls -la $out | grep ${tag}
+# second source for the shared-memory roofline denominator: ncu's own wavefront counter on the LDS.128 microbenchmark
+ncu --metrics l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.per_second,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,sm__cycles_elapsed.max \
+    --clock-control none -k regex:smem_bw_kernel --csv --log-file $out/${tag}_smem_microbench_ncu.csv python - > $out/${tag}_smem_microbench.log 2>&1 <<PY
+import ctypes as C, torch
+from gym_cloth_b200 import lib as L
+torch.zeros(1, device="cuda")
+lib = L.lib(); v = C.c_double(0)
+lib.clothb200_bench_smem_bandwidth(2000, C.byref(v), None)
+print("clothb200_bench_smem_bandwidth: %.1f GB/s" % v.value)
+PY
+tail -3 $out/${tag}_smem_microbench.log

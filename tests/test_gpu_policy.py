@@ -129,20 +129,22 @@ def test_wrinkle_policy_matches_reference():
     from gym_cloth_b200 import cfg_path
     from gym_cloth_b200.envs import ClothEnv
     from gym_cloth_b200.policies import WrinklesPolicy
-    g = load_golden("policy_wrinkle_t1_s1337.npz")
-    env = ClothEnv(cfg_path(1), dtype="f64")
-    env.seed(int(g["seed"]))
-    policy = WrinklesPolicy()
-    policy.set_env_cfg(env, env.cfg)
-    obs = env.reset()
-    assert np.array_equal(obs.reshape(-1, 3), g["pos_reset_e0"])
-    for k in range(int(g["episode_lengths"][0])):
-        a = policy.get_action(obs, k)
-        assert np.array_equal(np.array(a, np.float64), g["action_%d" % k]), (k, a, g["action_%d" % k])
-        obs, rew, done, info = env.step(a)
-        rew_ref, done_ref, cov_ref, sim_ref = g["result_%d" % k]
-        assert np.array_equal(obs.reshape(-1, 3), g["pos_%d" % k])
-        assert abs(rew - rew_ref) < 1e-11 and done == bool(done_ref) and info["num_sim_steps"] == int(sim_ref)
+    for tier, name in ((1, "policy_wrinkle_t1_s1337.npz"), (3, "policy_wrinkle_t3_s1337.npz")):
+        g = load_golden(name)
+        env = ClothEnv(cfg_path(tier), dtype="f64")
+        env.seed(int(g["seed"]))
+        np.random.seed(int(g["seed"]))                 # the generator seeds the global stream before reset (dom-rand draws)
+        policy = WrinklesPolicy()
+        policy.set_env_cfg(env, env.cfg)
+        obs = env.reset()
+        assert np.array_equal(obs.reshape(-1, 3), g["pos_reset_e0"])
+        for k in range(int(g["episode_lengths"][0])):
+            a = policy.get_action(obs, k)
+            assert np.array_equal(np.array(a, np.float64), g["action_%d" % k]), (tier, k, a, g["action_%d" % k])
+            obs, rew, done, info = env.step(a)
+            rew_ref, done_ref, cov_ref, sim_ref = g["result_%d" % k]
+            assert np.array_equal(obs.reshape(-1, 3), g["pos_%d" % k])
+            assert abs(rew - rew_ref) < 1e-11 and done == bool(done_ref) and info["num_sim_steps"] == int(sim_ref)
 
 
 def test_batched_wrinkle_policy_matches_single_env_policy():

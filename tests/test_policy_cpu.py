@@ -16,14 +16,15 @@ class _E(object):
 
 def test_wrinkle_policy_actions_on_reference_states():
     from gym_cloth_b200.policies import WrinklesPolicy, _neighbors, _wrinkle_levels
-    g = load_golden("policy_wrinkle_t1_s1337.npz")
     pol = WrinklesPolicy()
-    states = [g["pos_reset_e0"]] + [g["pos_%d" % k] for k in range(int(g["episode_lengths"][0]) - 1)]
-    for k, pos in enumerate(states):
-        env = _E(); env.cloth = _E(); env.cloth.pts = [_P(p) for p in pos]
-        pol.set_env_cfg(env, {})
-        a = np.array(pol.get_action(None, k), np.float64)
-        assert np.array_equal(a, g["action_%d" % k]), (k, a, g["action_%d" % k])
+    for name in ("policy_wrinkle_t1_s1337.npz", "policy_wrinkle_t3_s1337.npz"):     # 1 action (episode over) + 3 actions
+        g = load_golden(name)
+        states = [g["pos_reset_e0"]] + [g["pos_%d" % k] for k in range(int(g["episode_lengths"][0]) - 1)]
+        for k, pos in enumerate(states):
+            env = _E(); env.cloth = _E(); env.cloth.pts = [_P(p) for p in pos]
+            pol.set_env_cfg(env, {})
+            a = np.array(pol.get_action(None, k), np.float64)
+            assert np.array_equal(a, g["action_%d" % k]), (name, k, a, g["action_%d" % k])
     lv = _wrinkle_levels()
     assert len(lv) == 50 and lv[0] == 1 and lv[-1] > 0
     assert _neighbors(0, 0, 25, 25) == [0, 26, 25, 1] and len(_neighbors(12, 12, 25, 25)) == 9
