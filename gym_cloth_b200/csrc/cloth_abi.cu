@@ -71,11 +71,13 @@ const uint32_t *get_sweep_table(int W, int *levels, int *lw) {
             }
             size_t width = 0;
             for (auto &v : per_level) width = v.size() > width ? v.size() : width;
-            int w2 = 1; while (w2 < (int)width) w2 <<= 1;
-            Entry en{nullptr, (int)per_level.size(), w2};
-            if (w2 <= 32) {
-                std::vector<uint32_t> flat((size_t)en.levels * w2, 0xffffffffu);
-                for (int l = 0; l < en.levels; l++) for (size_t i = 0; i < per_level[l].size(); i++) flat[(size_t)l * w2 + i] = per_level[l][i];
+            // rows of 32 entries (one per lane), padded with empty rows to a multiple of eight levels plus eight more:
+            // limit_sweep() reads eight levels ahead without bounds or lane checks
+            Entry en{nullptr, (int)per_level.size(), 32};
+            if (width <= 32) {
+                const size_t rows = (((size_t)en.levels + 7) / 8) * 8 + 8;
+                std::vector<uint32_t> flat(rows * 32, 0xffffffffu);
+                for (int l = 0; l < en.levels; l++) for (size_t i = 0; i < per_level[l].size(); i++) flat[(size_t)l * 32 + i] = per_level[l][i];
                 if (cudaMalloc((void **)&en.dev, flat.size() * 4) == cudaSuccess)
                     cudaMemcpy(en.dev, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice);
                 else en.dev = nullptr;

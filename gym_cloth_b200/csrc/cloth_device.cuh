@@ -59,6 +59,8 @@ template <typename T> struct DevParams {
     T min_z, fric1, surf_off;    // minimum_z, 1-plane_friction, 1e-4 (cloth.pyx:345-370)
     T tear_thresh;
     T rest_k[6];                 // rest lengths of the flat grid per spring kind k (used when rest == NULL)
+    T kkrest_k[6];               // ks * kc * rest_k[k]: the constant of the f32 Hooke form kk - kkrest / l
+    T limit_c2_k[6];             // min(rest_k * 1.1, rest_k * tear_thresh)^2: squared length beyond which a spring needs the limit pass
     double grip_radius, thickness, gripper_height;
     double iu, iur, igr, ir;     // iters_up, iters_up_rest, iters_grip_rest, iters_rest
     // static wavefront schedule of _limit_spring_changes: springs grouped by dependency level (level(s) = 1 + max level
@@ -285,6 +287,11 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         if (REST_TABLE) return __ldg(rest + q * 6 + k);
         return sel6(P.rest_k, k);
     }
+    // kk * rest of spring (q, k): a launch constant unless the cloth carries its own rest lengths
+    __device__ __forceinline__ T kkrest_of(int q, int k, T kk) const {
+        if (REST_TABLE || !FAST) return kk * rest_of(q, k);
+        return P.kkrest_k[k];
+    }
     __device__ __forceinline__ T kk_of(int k) const { return k >= 4 ? P.kk_bend : P.kk_struct; }
 
     // ---- distance predicates ----
@@ -312,14 +319,14 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // One spring's contribution to point p, selected without branches so that the 12 neighbour loads and
     // the 12 independent force evaluations of a point can overlap.  SIGN=+1: p is ptA, -1: p is ptB.
     template <int SIGN>
-    __device__ __forceinline__ void add_spring(bool valid, const P4 &Pa, const P4 &Pb, T kk, T rst, T &fx, T &fy, T &fz, int &bad) {
+    __device__ __forceinline__ void add_spring(bool valid, const P4 &Pa, const P4 &Pb, T kk, T rst, T kkrst, T &fx, T &fy, T &fz, int &bad) {
         const T d0 = Pb.x - Pa.x, d1 = Pb.y - Pa.y, d2 = Pb.z - Pa.z;
         const T q = d0 * d0 + d1 * d1 + d2 * d2;
         T fm;
         if (FAST) {
             // ks*kc*(l-rest)/l; a spring that does not exist gets coefficient 0, a zero-length one gives inf -> NaN
             // positions, which commit_and_hash() reports as BADSTATE (the reference raises ZeroDivisionError here)
-            fm = valid ? kk - (kk * rst) * rsqrtf((float)q) : T(0);
+            fm = valid ? kk - kkrst * rsqrtf((float)q) : T(0);
             if (SIGN > 0) { fx += fm * d0; fy += fm * d1; fz += fm * d2; }
             else { fx -= fm * d0; fy -= fm * d1; fz -= fm * d2; }
             return;
@@ -354,20 +361,20 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             // _reset_gravity: f = 0 then f += (0,0,mg)
             T fx = T(0) + T(0), fy = T(0) + T(0), fz = T(0) + P.mg;
             // springs created by p (p is ptB, ptB.add_force(-F)), creation order k = 0..5
-            add_spring<-1>(v0, A0, Pp, P.kk_struct, rest_of(p, 0), fx, fy, fz, bad);
-            add_spring<-1>(v1, A1, Pp, P.kk_struct, rest_of(p, 1), fx, fy, fz, bad);
-            add_spring<-1>(v2, A2, Pp, P.kk_struct, rest_of(p, 2), fx, fy, fz, bad);
-            add_spring<-1>(v3, A3, Pp, P.kk_struct, rest_of(p, 3), fx, fy, fz, bad);
-            add_spring<-1>(v4, A4, Pp, P.kk_bend, rest_of(p, 4), fx, fy, fz, bad);
-            add_spring<-1>(v5, A5, Pp, P.kk_bend, rest_of(p, 5), fx, fy, fz, bad);
+            add_spring<-1>(v0, A0, Pp, P.kk_struct, rest_of(p, 0), kkrest_of(p, 0, P.kk_struct), fx, fy, fz, bad);
+            add_spring<-1>(v1, A1, Pp, P.kk_struct, rest_of(p, 1), kkrest_of(p, 1, P.kk_struct), fx, fy, fz, bad);
+            add_spring<-1>(v2, A2, Pp, P.kk_struct, rest_of(p, 2), kkrest_of(p, 2, P.kk_struct), fx, fy, fz, bad);
+            add_spring<-1>(v3, A3, Pp, P.kk_struct, rest_of(p, 3), kkrest_of(p, 3, P.kk_struct), fx, fy, fz, bad);
+            add_spring<-1>(v4, A4, Pp, P.kk_bend, rest_of(p, 4), kkrest_of(p, 4, P.kk_bend), fx, fy, fz, bad);
+            add_spring<-1>(v5, A5, Pp, P.kk_bend, rest_of(p, 5), kkrest_of(p, 5, P.kk_bend), fx, fy, fz, bad);
             // springs created by later points in which p is ptA, in creation order:
             // q = p+1 (k=1), p+2 (k=5), p+W-1 (k=3), p+W (k=0), p+W+1 (k=2), p+2W (k=4)
-            add_spring<1>(u0, Pp, B0, P.kk_struct, rest_of(u0 ? p + 1 : p, 1), fx, fy, fz, bad);
-            add_spring<1>(u1, Pp, B1, P.kk_bend, rest_of(u1 ? p + 2 : p, 5), fx, fy, fz, bad);
-            add_spring<1>(u2, Pp, B2, P.kk_struct, rest_of(u2 ? p + W - 1 : p, 3), fx, fy, fz, bad);
-            add_spring<1>(u3, Pp, B3, P.kk_struct, rest_of(u3 ? p + W : p, 0), fx, fy, fz, bad);
-            add_spring<1>(u4, Pp, B4, P.kk_struct, rest_of(u4 ? p + W + 1 : p, 2), fx, fy, fz, bad);
-            add_spring<1>(u5, Pp, B5, P.kk_bend, rest_of(u5 ? p + 2 * W : p, 4), fx, fy, fz, bad);
+            add_spring<1>(u0, Pp, B0, P.kk_struct, rest_of(u0 ? p + 1 : p, 1), kkrest_of(u0 ? p + 1 : p, 1, P.kk_struct), fx, fy, fz, bad);
+            add_spring<1>(u1, Pp, B1, P.kk_bend, rest_of(u1 ? p + 2 : p, 5), kkrest_of(u1 ? p + 2 : p, 5, P.kk_bend), fx, fy, fz, bad);
+            add_spring<1>(u2, Pp, B2, P.kk_struct, rest_of(u2 ? p + W - 1 : p, 3), kkrest_of(u2 ? p + W - 1 : p, 3, P.kk_struct), fx, fy, fz, bad);
+            add_spring<1>(u3, Pp, B3, P.kk_struct, rest_of(u3 ? p + W : p, 0), kkrest_of(u3 ? p + W : p, 0, P.kk_struct), fx, fy, fz, bad);
+            add_spring<1>(u4, Pp, B4, P.kk_struct, rest_of(u4 ? p + W + 1 : p, 2), kkrest_of(u4 ? p + W + 1 : p, 2, P.kk_struct), fx, fy, fz, bad);
+            add_spring<1>(u5, Pp, B5, P.kk_bend, rest_of(u5 ? p + 2 * W : p, 4), kkrest_of(u5 ? p + 2 * W : p, 4, P.kk_bend), fx, fy, fz, bad);
             // Verlet: new = x + damp*(x-px) + f*dsdm
             T nx = Pp.x + (P.damp * (Pp.x - Q.x)) + (fx * P.dsdm);
             T ny = Pp.y + (P.damp * (Pp.y - Q.y)) + (fy * P.dsdm);
@@ -899,8 +906,12 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         const T a = rst * T(1.1), b = rst * P.tear_thresh;
         return a < b ? a : b;
     }
-    __device__ __forceinline__ bool spring_flagged(const P4 &Pa, const P4 &Pb, T rst) const {
+    __device__ __forceinline__ bool spring_flagged(const P4 &Pa, const P4 &Pb, T rst, int k) const {
         if (Pa.w != T(0) && Pb.w != T(0)) return false;
+        if (FAST && !REST_TABLE) {       // per-kind constant: the same product limit_c() forms, squared once on the host side
+            const T d0 = Pa.x - Pb.x, d1 = Pa.y - Pb.y, d2 = Pa.z - Pb.z;
+            return d0 * d0 + d1 * d1 + d2 * d2 > P.limit_c2_k[k];
+        }
         return longer_than(Pa.x - Pb.x, Pa.y - Pb.y, Pa.z - Pb.z, limit_c(rst));
     }
     // snapshot test of all springs; also clears the hash table for the next substep
@@ -916,12 +927,12 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
             const P4 A0 = pos[v0 ? p - W : p], A1 = pos[v1 ? p - 1 : p], A2 = pos[v2 ? p - W - 1 : p];
             const P4 A3 = pos[v3 ? p - W + 1 : p], A4 = pos[v4 ? p - 2 * W : p], A5 = pos[v5 ? p - 2 : p];
             uint32_t bits = 0;
-            bits |= (v0 && spring_flagged(A0, Pb, rest_of(p, 0))) ? 1u : 0u;
-            bits |= (v1 && spring_flagged(A1, Pb, rest_of(p, 1))) ? 2u : 0u;
-            bits |= (v2 && spring_flagged(A2, Pb, rest_of(p, 2))) ? 4u : 0u;
-            bits |= (v3 && spring_flagged(A3, Pb, rest_of(p, 3))) ? 8u : 0u;
-            bits |= (v4 && spring_flagged(A4, Pb, rest_of(p, 4))) ? 16u : 0u;
-            bits |= (v5 && spring_flagged(A5, Pb, rest_of(p, 5))) ? 32u : 0u;
+            bits |= (v0 && spring_flagged(A0, Pb, rest_of(p, 0), 0)) ? 1u : 0u;
+            bits |= (v1 && spring_flagged(A1, Pb, rest_of(p, 1), 1)) ? 2u : 0u;
+            bits |= (v2 && spring_flagged(A2, Pb, rest_of(p, 2), 2)) ? 4u : 0u;
+            bits |= (v3 && spring_flagged(A3, Pb, rest_of(p, 3), 3)) ? 8u : 0u;
+            bits |= (v4 && spring_flagged(A4, Pb, rest_of(p, 4), 4)) ? 16u : 0u;
+            bits |= (v5 && spring_flagged(A5, Pb, rest_of(p, 5), 5)) ? 32u : 0u;
             if (bits) {
                 const int s = p * 6;
                 const int sh = s & 31;
@@ -1051,26 +1062,30 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
     // springs are stretched.  Used when the queue is long.
     // one dependency level of the sweep.  f32: branch-free (idle lanes run a dummy spring 0-0, the correction factor is
     // computed unconditionally and stores are predicated), because divergence is what a lone warp pays most for.
-    __device__ __forceinline__ int sweep_level(uint32_t cur, T rst_tab) {
+    __device__ __forceinline__ int sweep_level(uint32_t cur, T rst_tab, int &torn_acc) {
         if (FAST) {
+            // idle lanes run a pinned-pinned dummy spring between two copies of a point nobody writes (misc[8..11] =
+            // (0,0,0,1)): no predication anywhere, and no lane reads a point another lane may be storing
             const bool on = cur != 0xffffffffu;
-            const int a = on ? (int)(cur & 0xfffu) : 0, q = on ? (int)((cur >> 12) & 0xfffu) : 0, k = (cur >> 24) & 7u;
-            P4 Pa = mk4(T(0), T(0), T(0), T(1)), Pb = Pa;            // idle lanes: a pinned dummy spring, nothing read or written
-            if (on) { Pa = pos[a]; Pb = pos[q]; }
+            const uint32_t dummy = (uint32_t)(reinterpret_cast<const unsigned char *>(misc + 8) - reinterpret_cast<const unsigned char *>(pos));
+            const uint32_t ao = on ? (cur & 0xfffu) * (uint32_t)sizeof(P4) : dummy, qo = on ? ((cur >> 12) & 0xfffu) * (uint32_t)sizeof(P4) : dummy;
+            const int k = (cur >> 24) & 7u;
+            P4 *pa_ptr = reinterpret_cast<P4 *>(reinterpret_cast<unsigned char *>(pos) + ao), *pb_ptr = reinterpret_cast<P4 *>(reinterpret_cast<unsigned char *>(pos) + qo);
+            const P4 Pa = *pa_ptr, Pb = *pb_ptr;
             float c11, ct2;
             if (REST_TABLE) { c11 = (float)rst_tab * 1.1f; const float ct = (float)rst_tab * (float)P.tear_thresh; ct2 = ct * ct; }
             else { const float2 c = kc[k]; c11 = c.x; ct2 = c.y; }
             const bool pa = Pa.w != T(0), pb = Pb.w != T(0);
             const float e0 = (float)(Pa.x - Pb.x), e1 = (float)(Pa.y - Pb.y), e2 = (float)(Pa.z - Pb.z);
             const float qd = e0 * e0 + e1 * e1 + e2 * e2;
-            const bool live = on && !(pa && pb);
+            const bool live = !(pa && pb);
             const bool str = live && qd > c11 * c11;
-            if (live && qd > ct2) misc[2] = 1;
+            torn_acc |= (live && qd > ct2) ? 1 : 0;
             const float fac = 1.0f - c11 * rsqrtf(fmaxf(qd, 1e-30f));
-            const float fa = pa ? 0.0f : (pb ? fac : fac * 0.5f);
-            const float fb = pb ? 0.0f : (pa ? fac : fac * 0.5f);
-            if (str && !pa) pos[a] = mk4((T)((float)Pa.x - e0 * fa), (T)((float)Pa.y - e1 * fa), (T)((float)Pa.z - e2 * fa), Pa.w);
-            if (str && !pb) pos[q] = mk4((T)((float)Pb.x + e0 * fb), (T)((float)Pb.y + e1 * fb), (T)((float)Pb.z + e2 * fb), Pb.w);
+            const float half = fac * 0.5f;
+            const float fa = pb ? fac : half, fb = pa ? fac : half;      // a pinned end is never stored
+            if (str && !pa) *pa_ptr = mk4((T)((float)Pa.x - e0 * fa), (T)((float)Pa.y - e1 * fa), (T)((float)Pa.z - e2 * fa), Pa.w);
+            if (str && !pb) *pb_ptr = mk4((T)((float)Pb.x + e0 * fb), (T)((float)Pb.y + e1 * fb), (T)((float)Pb.z + e2 * fb), Pb.w);
             __syncwarp();
             return str ? 1 : 0;
         }
@@ -1107,24 +1122,26 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
         return __ldg(rest + ((e >> 12) & 0xfffu) * 6 + ((e >> 24) & 7u));
     }
     __device__ __forceinline__ void limit_sweep() {
-        const int lw = P.sweep_lw, nl = P.sweep_levels;
-        const bool lane_on = lane < lw;
+        const int nl = P.sweep_levels;
+        // the schedule: rows of 32 entries (idle lanes and the padding rows hold ~0u), padded to a multiple of eight
+        // levels plus eight more, so that the loads below need neither bounds nor lane predicates.  Entries (and, with
+        // a rest table, the rest lengths) are fetched eight levels ahead: the table lives in L2, shared memory leaves
+        // little L1
         const uint32_t *tp = P.sweep_tbl + lane;
-        // schedule entries (and, with a rest table, the rest lengths) are fetched eight levels ahead: the table lives in
-        // L2, shared memory leaves little L1
         uint32_t cur[8], nxt[8];
         T rcur[8], rnxt[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) { cur[u] = (lane_on && u < nl) ? __ldg(tp + (size_t)u * lw) : 0xffffffffu; }
+        for (int u = 0; u < 8; u++) cur[u] = __ldg(tp + 32 * u);
 #pragma unroll
         for (int u = 0; u < 8; u++) rcur[u] = sweep_rest(cur[u]);
-        int nmove = 0;
+        int nmove = 0, torn = 0;
         for (int L = 0; L < nl; L += 8) {
+            tp += 256;
 #pragma unroll
-            for (int u = 0; u < 8; u++) nxt[u] = (lane_on && L + 8 + u < nl) ? __ldg(tp + (size_t)(L + 8 + u) * lw) : 0xffffffffu;
+            for (int u = 0; u < 8; u++) nxt[u] = __ldg(tp + 32 * u);
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                nmove += sweep_level(cur[u], rcur[u]);
+                nmove += sweep_level(cur[u], rcur[u], torn);
                 if (u == 3) {
 #pragma unroll
                     for (int v = 0; v < 8; v++) rnxt[v] = sweep_rest(nxt[v]);
@@ -1133,6 +1150,7 @@ template <typename T, int NT, int WC, bool REST_TABLE, bool COLOURED = false> st
 #pragma unroll
             for (int u = 0; u < 8; u++) { cur[u] = nxt[u]; rcur[u] = rnxt[u]; }
         }
+        if (torn) misc[2] = 1;
         for (int j = lane; j < P.ev_words; j += 32) ev[j] = 0u;
         nmove = __reduce_add_sync(0xffffffffu, nmove);
         if (lane == 0) {

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
     }
     for (int j = tid; j < P.table_size; j += NT) { c.tkey[j] = CLOTH_KEY_EMPTY; c.tinfo[j] = 0u; }
     for (int j = tid; j < P.ev_words; j += NT) c.ev[j] = 0u;
-    if (tid < 16) { c.misc[tid] = 0; c.pacc[tid] = 0; }
+    // misc[8..11]: a pinned point at the origin that nobody writes - the idle lanes of the f32 sweep read it
+    if (tid < 16) { c.misc[tid] = (tid == 11 && sizeof(T) == 4) ? 0x3f800000 : 0; c.pacc[tid] = 0; }
     if (tid < 8) {
         const float r = (float)P.rest_k[tid < 6 ? tid : 0], ct = r * (float)P.tear_thresh;
         c.kc[tid] = make_float2(r * 1.1f, ct * ct);
@@ -421,7 +422,12 @@ template <typename T> int make_dev_params(const ClothB200Params &hp, DevParams<T
     P.tear_thresh = (T)hp.tear_thresh;
     const double diag = sqrt(dx * dx + dy * dy);
     const double rk[6] = {dx, dy, diag, diag, 2 * dx, 2 * dy};
-    for (int k = 0; k < 6; k++) P.rest_k[k] = (T)rk[k];
+    for (int k = 0; k < 6; k++) {
+        P.rest_k[k] = (T)rk[k];
+        P.kkrest_k[k] = (k >= 4 ? P.kk_bend : P.kk_struct) * P.rest_k[k];
+        const T a = P.rest_k[k] * T(1.1), b = P.rest_k[k] * P.tear_thresh, c = a < b ? a : b;    // ClothCTA::limit_c
+        P.limit_c2_k[k] = c * c;
+    }
     P.grip_radius = hp.grip_radius; P.thickness = hp.thickness; P.gripper_height = hp.gripper_height;
     int nlev = 0;
     for (double z = hp.gripper_height; z > 0; z -= hp.thickness) { nlev++; if (nlev > 8 * ts / 8) break; }
