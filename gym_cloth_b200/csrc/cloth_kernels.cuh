@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
         // (then the launch ends at max(longest action, total work / slots) instead of with the last whole action) ----
         // (ordering by measured time left instead - substeps left x this action's cycles per substep - was tried and is
         // worse: the FIFO of waiting cloths stays sorted by substeps left, not by such estimates, and long cloths starve)
-        if (tid == 0) { s_item[0] = iterations - i; s_item[1] = queue_head_remaining(A) > iterations - i ? 1 : 0; }
+        if (tid == 0) { s_item[0] = iterations - i; s_item[1] = queue_head_remaining(A) > iterations - i + A.yield_slack ? 1 : 0; }
         c.sync();
         const bool yield = s_item[1] != 0;
         const int left_units = s_item[0];
@@ -471,7 +471,7 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
         if (A.n_env > use_slots) {
             queue_init_kernel<<<(A.n_env + 255) / 256, 256, 0, st>>>(A.n_env, A.sorted_keys, A.queue, A.qctl, A.progress, A.ngrab_s, A.cycles_s);
             StepArgs<T> B = A;
-            if (g_force_slice > 0) B.slice = g_force_slice;
+            if (g_force_slice > 0) { B.slice = g_force_slice; B.yield_slack = 0; }
             kern<<<use_slots, NT, smem, st>>>(P, B);
             g_launch_count += 2;
             cudaError_t e = cudaGetLastError();
@@ -489,6 +489,7 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
 }
 
 int slice_substeps();           // cloth_abi.cu: CLOTHB200_SLICE env var; default 64, 0 = whole actions
+int yield_slack_substeps();     // cloth_abi.cu: CLOTHB200_YIELD_SLACK env var (substeps)
 int threads_per_cloth(int W);   // cloth_abi.cu: CLOTHB200_NT env var; default 128 (512 for 64x64)
 
 template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {
