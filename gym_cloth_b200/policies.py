@@ -1,6 +1,6 @@
 """Analytic policies that drive the hot path, restated from examples/analytic.py.
 
-`OracleCornerPolicy` / `RandomPolicy` keep the reference's interface (`set_env_cfg(env, cfg)`, `get_action(obs, t)`)
+`OracleCornerPolicy`, `OracleCornerRevealPolicy`, `HighestPointPolicy`, `WrinklesPolicy`, `RandomPolicy` keep the reference's interface (`set_env_cfg(env, cfg)`, `get_action(obs, t)`)
 for the single-env facade; `oracle_corner_actions(benv)` is the batched form: one action per environment computed on
 the device from the four near-corner points (indices 26, 48, 576, 598; analytic.py:109-125)."""
 import numpy as np
@@ -57,6 +57,46 @@ class OracleCornerPolicy(Policy):
         return (cx, cy, dx, dy) if self.cfg["env"]["clip_act_space"] else (x, y, dx, dy)
 
 
+class OracleCornerRevealPolicy(Policy):
+    """analytic.py:217-358 ('alg1', delta actions): the oracle corner policy restricted to the corners the camera can see
+    (`env._occlusion_vec`, order ur, lr, ll, ul; True = occluded) - while a visible corner is further than 0.09 from its
+    target it is pulled there; otherwise the occluded corner furthest from its target is pulled AWAY from the target by
+    half a bed width, to reveal it.  The vector is whatever the environment holds: the reference fills it from Blender's
+    ray casts when it renders (cloth_env.py:287-292) and leaves it all-True otherwise (:115), as this package does."""
+
+    def __init__(self):
+        self._sign = 1
+
+    def get_action(self, obs, t):
+        if not self.cfg["env"]["delta_actions"]:
+            raise NotImplementedError("the reference discourages the no-delta variant")
+        pts = self.env.cloth.pts
+        assert len(pts) == 625, len(pts)
+        flipped = self.cfg["init"]["type"] == "tier2" and (not self.env.cloth.init_side)
+        data = []
+        for idx, (tx, ty) in zip(_corner_indices(flipped), _TARGETS):
+            x, y = pts[idx].x, pts[idx].y
+            data.append((x, y, (x - 0.5) * 2.0, (y - 0.5) * 2.0, (tx - x) * 0.90, (ty - y) * 0.90, np.sqrt((x - tx) ** 2 + (y - ty) ** 2)))
+        occ = list(self.env._occlusion_vec)
+        distances = [d[6] for d in data]
+        vis = [d if not occ[i] else 0 for i, d in enumerate(distances)]
+        hid = [d if occ[i] else 0 for i, d in enumerate(distances)]
+        maxvis, maxhid = max(vis), max(hid)
+        thresh_dist = 0.09
+        if (False in occ and maxvis > thresh_dist) or (True not in occ and maxvis < thresh_dist):
+            maxdist, distances, self._sign = maxvis, vis, 1
+        else:
+            maxdist, distances, self._sign = maxhid, hid, -1
+        x, y, cx, cy, dx, dy, _ = next(d for d, dist in zip(data, distances) if dist == maxdist)   # first corner at the maximum
+        if self._sign == -1:
+            scaling_factor = 0.5 / maxdist
+            dx *= scaling_factor
+            dy *= scaling_factor
+        if self.cfg["env"]["clip_act_space"]:
+            return (cx, cy, dx * self._sign, dy * self._sign)
+        return (x, y, dx * self._sign, dy * self._sign)
+
+
 class HighestPointPolicy(Policy):
     """Pull one of the `top_k` highest points (chosen with the global np.random, as the reference does) 90 % of the
     way to where that point sits on the flat grid (analytic.py:716-808)."""
@@ -107,6 +147,32 @@ def oracle_corner_actions(benv):
     tsel = targ[0][k]
     act = torch.cat([(sel - 0.5) * 2.0, (tsel - sel) * 0.90], dim=1)
     return act.to(c.dtype)
+
+
+def oracle_corner_reveal_actions(benv, occlusion):
+    """Batched OracleCornerRevealPolicy: `occlusion` [n_env, 4] bool (ur, lr, ll, ul; True = occluded) -> [n_env, 4] actions."""
+    c = benv.cloth
+    pos = c.pos
+    n = benv.n_env
+    dev = pos.device
+    occ = torch.as_tensor(occlusion, device=dev).bool().reshape(n, 4)
+    flipped = torch.as_tensor((benv.init_type == "tier2") & (~benv.init_side), device=dev)
+    idx = torch.where(flipped[:, None], torch.tensor(_corner_indices(True), device=dev)[None, :],
+                      torch.tensor(_corner_indices(False), device=dev)[None, :])
+    ar = torch.arange(n, device=dev)
+    xy = pos[ar[:, None], idx, :2].double()
+    targ = torch.tensor(_TARGETS, dtype=torch.float64, device=dev)[None]
+    dist = ((xy - targ) ** 2).sum(-1).sqrt()
+    vis = torch.where(occ, torch.zeros_like(dist), dist); hid = torch.where(occ, dist, torch.zeros_like(dist))
+    maxvis = vis.max(dim=1).values
+    pull = ((~occ).any(dim=1) & (maxvis > 0.09)) | ((~occ).all(dim=1) & (maxvis < 0.09))
+    d = torch.where(pull[:, None], vis, hid)
+    maxd = d.max(dim=1, keepdim=True).values
+    k = torch.argmax((d == maxd).to(torch.int8), dim=1)
+    sel = xy[ar, k]
+    delta = (targ[0][k] - sel) * 0.90
+    scale = torch.where(pull, torch.ones_like(maxd[:, 0]), -0.5 / maxd[:, 0])
+    return torch.cat([(sel - 0.5) * 2.0, delta * scale[:, None]], dim=1).to(c.dtype)
 
 
 def highest_point_actions(benv, top_k=5, generator=None):

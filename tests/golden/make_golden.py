@@ -291,6 +291,37 @@ def gen_policy(out, tier=1, seed=1337, episodes=2, kind="oracle", max_t=None):
     np.savez_compressed(os.path.join(out, "policy_%s_t%d_s%d.npz" % (kind, tier, seed)), **d)
 
 
+def gen_policy_reveal(out, tier=3, seed=1337):
+    """OracleCornerRevealPolicy (analytic.py:217-358) on reference states with the occlusion vectors Blender would
+    supply set by hand (the policy only reads env._occlusion_vec): every one of the 16 vectors on two states."""
+    sys.path.insert(0, os.path.join(REFERENCE, "examples"))
+    tmp = tempfile.mkdtemp(prefix="golden_rev_")
+    env = _make_env(tier, seed, tmp)
+    import contextlib, io, itertools
+    with contextlib.redirect_stdout(io.StringIO()):
+        import analytic
+    policy = analytic.OracleCornerRevealPolicy()
+    policy.set_env_cfg(env, env.cfg)
+    np.random.seed(seed)
+    env.reset()
+    d = {"tier": tier, "seed": seed}
+    states, occs, acts = [], [], []
+    for rep in range(2):
+        pos = _state(env.cloth)[0]
+        for occ in itertools.product([False, True], repeat=4):
+            env._occlusion_vec = list(occ)
+            with contextlib.redirect_stdout(io.StringIO()):
+                a = policy.get_action(None, 0)
+            states.append(pos); occs.append(occ); acts.append([float(v) for v in a])
+        env._occlusion_vec = [True, True, True, True]
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = policy.get_action(None, 0)
+        env.step(a)
+    d["pos"] = np.array(states); d["occlusion"] = np.array(occs); d["actions"] = np.array(acts)
+    np.savez_compressed(os.path.join(out, "policy_reveal_t%d_s%d.npz" % (tier, seed)), **d)
+    print("reveal policy: %d (state, occlusion) -> action samples" % len(acts))
+
+
 def gen_state(out, tier=1, seed=1337):
     """save_state / start_state_path (cloth_env.py:343-350, 120-124, 736-741): the reference env pickles its
     {"pts", "springs"} after one action; a second reference env starts from that file, resets and steps."""
@@ -440,7 +471,7 @@ def gen_tear(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "policy_wrinkle", "state", "bench_pool"])
+    ap.add_argument("what", choices=["all", "kat", "phases", "decode", "tear", "env", "policy", "policy_highest", "policy_wrinkle", "policy_reveal", "state", "bench_pool"])
     ap.add_argument("--tier", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--actions", type=int, default=3)
@@ -462,6 +493,8 @@ def main():
         sys.exit(max(rc))
     if a.what == "policy_highest":
         return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="highest", max_t=3)
+    if a.what == "policy_reveal":
+        return gen_policy_reveal(a.out, tier=a.tier, seed=a.seed)
     if a.what == "policy_wrinkle":      # WrinklesPolicy (analytic.py:551-720): ground-truth state, no image, no RNG
         return gen_policy(a.out, tier=a.tier, seed=a.seed, episodes=1, kind="wrinkle", max_t=3)
     {"kat": gen_kat, "phases": gen_phases, "decode": gen_decode, "tear": gen_tear, "policy": gen_policy, "state": gen_state, "bench_pool": gen_bench_pool}.get(

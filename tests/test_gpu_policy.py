@@ -171,3 +171,32 @@ def test_batched_wrinkle_policy_matches_single_env_policy():
     benv.step(acts)                                   # the actions are valid env.step input
     torch.cuda.synchronize()
     assert int(((benv.cloth.flags & 4) != 0).sum().item()) <= n // 4        # most grips catch the cloth edge point aimed at
+
+
+def test_batched_reveal_policy_matches_single_env_policy():
+    from gym_cloth_b200 import cfg_path
+    from gym_cloth_b200.envs import BatchedClothEnv
+    from gym_cloth_b200.policies import OracleCornerRevealPolicy, oracle_corner_reveal_actions
+    n = 32
+    benv = BatchedClothEnv(cfg_path(3), n, dtype="f64", seed=77)
+    benv.reset()
+    rng = np.random.RandomState(3)
+    occ = rng.rand(n, 4) < 0.5
+    occ[0] = True; occ[1] = False                       # all occluded (the 1-D observation default) / all visible
+    acts = oracle_corner_reveal_actions(benv, occ)
+    assert acts.shape == (n, 4) and acts.dtype == torch.float64
+
+    class _P(object):
+        def __init__(s, xyz): s.x, s.y, s.z = (float(v) for v in xyz)
+
+    class _E(object):
+        pass
+    pol = OracleCornerRevealPolicy()
+    for e in range(n):
+        env = _E(); env.cloth = _E(); env.cloth.pts = [_P(p) for p in benv.cloth.pos[e, :, :3].cpu().numpy()]
+        env.cloth.init_side = True; env._occlusion_vec = [bool(v) for v in occ[e]]
+        pol.set_env_cfg(env, benv.cfg)
+        ref = np.array(pol.get_action(None, 0), np.float64)
+        assert np.allclose(acts[e].cpu().numpy(), ref, atol=1e-12), (e, occ[e], acts[e], ref)
+    benv.step(acts)
+    torch.cuda.synchronize()

@@ -28,3 +28,21 @@ def test_wrinkle_policy_actions_on_reference_states():
     lv = _wrinkle_levels()
     assert len(lv) == 50 and lv[0] == 1 and lv[-1] > 0
     assert _neighbors(0, 0, 25, 25) == [0, 26, 25, 1] and len(_neighbors(12, 12, 25, 25)) == 9
+
+
+def test_reveal_policy_actions_on_reference_states():
+    """OracleCornerRevealPolicy (analytic.py:217-358): the reference's policy asked for an action on two reference states
+    under each of the 16 occlusion vectors (tests/golden/policy_reveal_t3_s1337.npz) - ours must answer bit for bit."""
+    from gym_cloth_b200.policies import OracleCornerRevealPolicy
+    g = load_golden("policy_reveal_t3_s1337.npz")
+    pol = OracleCornerRevealPolicy()
+    cfg = {"env": {"delta_actions": True, "clip_act_space": True}, "init": {"type": "tier3"}}
+    seen_signs = set()
+    for pos, occ, act in zip(g["pos"], g["occlusion"], g["actions"]):
+        env = _E(); env.cloth = _E(); env.cloth.pts = [_P(p) for p in pos]; env.cloth.init_side = True
+        env._occlusion_vec = [bool(v) for v in occ]
+        pol.set_env_cfg(env, cfg)
+        a = np.array(pol.get_action(None, 0), np.float64)
+        assert np.array_equal(a, act), (occ, a, act)
+        seen_signs.add(pol._sign)
+    assert seen_signs == {1, -1} and len(g["actions"]) == 32
