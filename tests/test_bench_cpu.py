@@ -45,4 +45,5 @@ def test_draws_are_sharding_invariant_and_deterministic():
     assert np.array_equal(bench.actions_for_step(1337, 4, 0, 3000), raw)
     c = bench.restart_choice(1337, 3, 0, 50, 4096)
     assert np.array_equal(c, bench.restart_choice(1337, 3, 0, 50, 4096)) and c.max() < 4096
+    assert np.array_equal(bench.restart_choice(7, 2, 0, 3000, 500), np.concatenate([bench.restart_choice(7, 2, 0, 1234, 500), bench.restart_choice(7, 2, 1234, 3000, 500)]))
     assert bench.draw_actions(1, 0, 0, 16, n_points=4096)[1].max() < 4096
