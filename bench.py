@@ -219,10 +219,13 @@ class Arm(object):
         self.aim = args.actions == "touch_cloth"
 
     # -- pool restarts
-    def restart(self, t, done_idx):
+    def choice_for(self, t):
+        return self.torch.from_numpy(restart_choice(self.args.seed, t, self.lo, self.hi, self.n_pool)).to(self.c.device)
+
+    def restart(self, t, done_idx, choice=None):
         """Environments done_idx (device index tensor) restart from their pool states of step t."""
         c, torch = self.c, self.torch
-        k = torch.from_numpy(restart_choice(self.args.seed, t, self.lo, self.hi, self.n_pool)).to(c.device)[done_idx]
+        k = (self.choice_for(t) if choice is None else choice)[done_idx]
         c.pos[done_idx] = self.pool["pos"][k]; c.prev[done_idx] = self.pool["prev"][k]
         c.prev_coverage[done_idx] = self.pool["cov"][k]
         if "rest" in self.pool:
@@ -249,11 +252,12 @@ class Arm(object):
     def run_device(self, K, W, barrier, flush=None, sampler=None, t_base=0):
         torch, c = self.torch, self.c
         drawn = [self.device_actions(t_base + t) for t in range(W + K)]
+        choice = [self.choice_for(t_base + t) for t in range(W + K)]         # like the actions: resident before the clock starts
         for t in range(W):
             self.device_step(t, drawn[t])
             d = torch.nonzero(c.done)[:, 0]
             if d.numel():
-                self.restart(t_base + t, d)
+                self.restart(t_base + t, d, choice[t])
         barrier()
         if sampler is not None:
             sampler.start()
@@ -271,7 +275,7 @@ class Arm(object):
             sub += c.sim_steps.sum(); nog += ((c.flags & 4) != 0).sum(); dn += (c.done != 0).sum()
             d = torch.nonzero(c.done)[:, 0]            # (a masked, sync-free restart was measured: 1 % slower end to end)
             if d.numel():
-                self.restart(t_base + W + t, d)
+                self.restart(t_base + W + t, d, choice[W + t])
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler is not None else None

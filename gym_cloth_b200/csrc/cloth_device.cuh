@@ -100,6 +100,7 @@ template <typename T> struct StepArgs {
     // tickets from a queue, runs `slice` substeps of that cloth, stores it and re-queues it behind everything else
     int slice, qcap;
     int yield_slack;             // a cloth keeps its slot unless the waiting one has more than this many substeps more left
+    int endgame_slices, endgame_shift;   // the last endgame_slices slices of an action run in slices of slice >> endgame_shift
     unsigned long long *queue;   // [qcap] (ticket + 1) << 32 | substeps left << 16 | item
     const unsigned long long *sorted_keys;   // plan_work_kernel's keys after the sort (substeps per item)
     int *qctl;                   // [0] tickets taken, [1] tickets issued, [2] cloths finished

@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
         if (A.grab_mask) c.write_grab_mask(A.grab_mask + (size_t)env * ((N + 31) >> 5));
     }
     bool released = stepping && i_begin > e3;
-    int i_end = sliced ? min(iterations, i_begin + A.slice) : iterations;
+    // slices and the swap hysteresis shrink to a quarter for the last six slices of an action: the launch ends when its last
+    // cloth does, and near the end the grain of the hand-over is what the slots differ by
+    const int endgame = A.endgame_slices * A.slice;
+    auto slice_len = [&](int left) { return left <= endgame ? max(A.slice >> A.endgame_shift, 1) : A.slice; };
+    int i_end = sliced ? min(iterations, i_begin + slice_len(iterations - i_begin)) : iterations;
     const long long t_loop0 = clock64();
     int i = i_begin;
     bool broke = false, parked = false;
@@ -133,12 +137,15 @@ __global__ void __launch_bounds__(NT, MinBlocks<T, NT>::v) cloth_step_kernel(con
         // (then the launch ends at max(longest action, total work / slots) instead of with the last whole action) ----
         // (ordering by measured time left instead - substeps left x this action's cycles per substep - was tried and is
         // worse: the FIFO of waiting cloths stays sorted by substeps left, not by such estimates, and long cloths starve)
-        if (tid == 0) { s_item[0] = iterations - i; s_item[1] = queue_head_remaining(A) > iterations - i + A.yield_slack ? 1 : 0; }
+        if (tid == 0) {
+            const int left = iterations - i, slack = left <= endgame ? A.yield_slack >> A.endgame_shift : A.yield_slack;
+            s_item[0] = left; s_item[1] = queue_head_remaining(A) > left + slack ? 1 : 0;
+        }
         c.sync();
         const bool yield = s_item[1] != 0;
         const int left_units = s_item[0];
         c.sync();
-        if (!yield) { i_end = min(iterations, i + A.slice); continue; }
+        if (!yield) { i_end = min(iterations, i + slice_len(left_units)); continue; }
         const int bad_now = c.misc[3];
         fence_async_smem();
         c.sync();
@@ -471,7 +478,7 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
         if (A.n_env > use_slots) {
             queue_init_kernel<<<(A.n_env + 255) / 256, 256, 0, st>>>(A.n_env, A.sorted_keys, A.queue, A.qctl, A.progress, A.ngrab_s, A.cycles_s);
             StepArgs<T> B = A;
-            if (g_force_slice > 0) { B.slice = g_force_slice; B.yield_slack = 0; }
+            if (g_force_slice > 0) { B.slice = g_force_slice; B.yield_slack = 0; B.endgame_slices = 0; }
             kern<<<use_slots, NT, smem, st>>>(P, B);
             g_launch_count += 2;
             cudaError_t e = cudaGetLastError();
@@ -490,6 +497,8 @@ template <typename T, int NT, int WC, bool RT, bool COL> int launch_step_inst(co
 
 int slice_substeps();           // cloth_abi.cu: CLOTHB200_SLICE env var; default 64, 0 = whole actions
 int yield_slack_substeps();     // cloth_abi.cu: CLOTHB200_YIELD_SLACK env var (substeps)
+int endgame_slices();           // cloth_abi.cu: CLOTHB200_ENDGAME env var (slices), CLOTHB200_ENDGAME_SHIFT
+int endgame_shift();
 int threads_per_cloth(int W);   // cloth_abi.cu: CLOTHB200_NT env var; default 128 (512 for 64x64)
 
 template <typename T, int WC, bool RT, bool COL> int launch_step_nt(const DevParams<T> &P, const StepArgs<T> &A, cudaStream_t st) {

@@ -68,7 +68,7 @@ int step_plans_t(const ClothB200Params *hp, int mode, int n_env, const ClothB200
             A.ngrab_s = A.progress + n_env;
             A.cycles_s = (float *)(A.ngrab_s + n_env);
             A.qctl = (int *)(A.cycles_s + n_env);
-            A.slice = slice; A.yield_slack = yield_slack_substeps(); A.qcap = n_env; A.sorted_keys = keys;
+            A.slice = slice; A.yield_slack = yield_slack_substeps(); A.endgame_slices = endgame_slices(); A.endgame_shift = endgame_shift(); A.qcap = n_env; A.sorted_keys = keys;
         }
     }
     return launch_step<T>(*hp, A, st, mode);
