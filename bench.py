@@ -421,6 +421,9 @@ def run_ours(args):
                           "time-sliced launch)" % (n * c.N * 8 * esz // 2 ** 20)},
             "roofline": {"bound": "smem", "achieved": smem_ach, "peak": smem_peak.value, "unit": "GB/s",
                          "frac": smem_ach / smem_peak.value if smem_peak.value else None, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (x envs): 40 KB per env-step are the one "
+                                         "load and store of the state, the rest are the 40 KB swaps of the time-sliced launch (DESIGN.md 4); "
+                                         "HBM runs at < 0.1 % of its peak either way",
                          "kernel": "cloth_step_kernel", "kernel_ms_per_launch": kernel_ms / K,
                          "algorithmic_bytes_per_substep": b_sub, "substeps_per_launch": total_substeps / world / K,
                          "peak_source": "LDS.128 streaming microbenchmark run in this process (clothb200_bench_smem_bandwidth; its ncu "
